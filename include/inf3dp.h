@@ -1,0 +1,119 @@
+/* inf3dp.h -- C ABI of the B200-native INF-3DP hot path (libinf3dp.so, sm_100a only).
+ *
+ * Plain pointers and sizes, no torch types.  Every pointer argument is a DEVICE pointer unless its name ends
+ * in `_host`.  Inputs are borrowed and never written; outputs and workspaces are allocated by the caller
+ * (the Python shim allocates them as torch tensors); kernels never allocate.  All entry points are
+ * asynchronous on `stream` unless stated, re-entrant, and return 0 on success or an INF3DP_E* code, with a
+ * human-readable message available from inf3dp_last_error() (thread-local).  There is no CPU fallback.
+ *
+ * Each entry point names the reference interface it replaces (paths relative to the INF-3DP repository).
+ */
+#ifndef INF3DP_H_
+#define INF3DP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* inf3dp_stream_t; /* == cudaStream_t */
+
+enum {
+    INF3DP_OK = 0,
+    INF3DP_EINVAL = 1,      /* bad argument (shape, null pointer, unsupported configuration) */
+    INF3DP_ECUDA = 2,       /* a CUDA runtime call or kernel launch failed                   */
+    INF3DP_EWORKSPACE = 3,  /* workspace too small (see the *_workspace_bytes query)          */
+    INF3DP_EOVERFLOW = 4    /* data-dependent capacity exceeded (reported by *_status)       */
+};
+
+enum { INF3DP_ACT_SINE = 0, INF3DP_ACT_RELU = 1 };
+
+/* Execution engine of inf3dp_siren_jet. */
+enum {
+    INF3DP_MODE_AUTO = 0,       /* TC_PRECISE when the configuration supports it, else SIMT           */
+    INF3DP_MODE_SIMT = 1,       /* FP32 CUDA-core kernel: any supported configuration, orders 0..2     */
+    INF3DP_MODE_TC_PRECISE = 2, /* tcgen05 tensor cores, FP16 hi/lo split operands (3 MMAs), FP32 acc. */
+    INF3DP_MODE_TC_FAST = 3     /* tcgen05 tensor cores, single FP16 operands (does NOT meet 0.1 deg)  */
+};
+
+const char* inf3dp_last_error(void);
+int inf3dp_version(void);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * SIREN field network.  Replaces modules.py:143-160 (SingleBVPNet.forward -> FCBlock -> BatchLinear + Sine)
+ * together with what diff_operators.py:128-132 (gradient) and :27-44 (hessian3d) extract from it by autograd.
+ *
+ * Network: in_features -> hidden (act) -> [hidden -> hidden (act)] x num_hidden_layers -> out_features (linear),
+ * act = sin(omega0 * z) (modules.py:34) or max(z, 0) (exp_scripts/train_levels.py:35-51).
+ * Supported: hidden == 256, in_features in {3, 4}, 1 <= out_features <= 64, num_hidden_layers >= 0.
+ * ------------------------------------------------------------------------------------------------------- */
+
+/* Size of the packed-weights blob for a configuration (0 if unsupported). */
+size_t inf3dp_siren_packed_bytes(int in_features, int hidden, int num_hidden_layers, int out_features);
+
+/* Pack a state_dict once: folds omega0 into the sine layers in FP32 and writes the operand images every
+ * engine needs (FP32 transposed weights for SIMT; FP16 hi/lo UMMA shared-memory images for tcgen05).
+ * weights_host / biases_host: host arrays of (num_hidden_layers + 2) DEVICE pointers, layer i of shape
+ * [out_i, in_i] row-major / [out_i] -- the tensors behind the reference keys net.net.{i}.0.weight / .bias. */
+int inf3dp_siren_pack_weights(const float* const* weights_host, const float* const* biases_host, int in_features,
+                              int hidden, int num_hidden_layers, int out_features, int activation, float omega0,
+                              void* packed, size_t packed_bytes, inf3dp_stream_t stream);
+
+/* Batched field query with forward-mode derivatives ("jet").
+ *   x [n, in_features] -> y [n, out];  order >= 1: J [n, out, 3] = dy/dx;  order == 2: H [n, out, 3, 3].
+ * Derivatives are taken with respect to the first three input features.  J / H may be NULL when order is lower.
+ * mode: INF3DP_MODE_*.  TC modes need the flagship configuration (sine, in 3, hidden 256, 3 hidden layers,
+ * out <= 8, order <= 1) and return INF3DP_EINVAL otherwise; AUTO falls back to SIMT for those. */
+int inf3dp_siren_jet(const void* packed, const float* x, int64_t n, int order, float* y, float* J, float* H,
+                     int mode, inf3dp_stream_t stream);
+
+/* Curvature tail.  Replaces the per-point Python loop of diff_operators.py:167-220 (min_max_curvs_and_vectors)
+ * and construct_tangent_basis (:280-298): grad [n,3], hess [n,3,3] -> kappa [n,2] (min,max), dirs [n,2,3]. */
+int inf3dp_principal_curvatures(const float* grad, const float* hess, int64_t n, float* kappa, float* dirs,
+                                inf3dp_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Isocontour extraction.  Replaces contour_cuda/ext.cpp:5-17 extract_isocontours
+ * (-> isocontours.cu:216-293: extract_contours_kernel :16-93 + merge_segments_kernel :99-213).
+ *   vertices [nV,3] f32, faces [nF,3] i32, fields [nV] f32, iso_values [K] f32
+ *   -> contours_merged [K, nF, 3] f32 (dense, zero padded, loops separated by (-1e9,-1e9,-1e9) rows),
+ *      contour_nums [K] i32.  Both outputs are fully written by the call (no pre-zeroing needed).
+ * Deterministic: equals the reference run with segments slotted in ascending face order.
+ * ------------------------------------------------------------------------------------------------------- */
+size_t inf3dp_extract_isocontours_workspace_bytes(int nV, int nF, int K);
+/* Same, but with a segment pool of at least `min_segments` (use after INF3DP_EOVERFLOW; a larger workspace
+ * passed to inf3dp_extract_isocontours is used automatically). */
+size_t inf3dp_extract_isocontours_workspace_bytes_segments(int nV, int nF, int K, int64_t min_segments);
+int inf3dp_extract_isocontours(const float* vertices, const int32_t* faces, const float* fields,
+                               const float* iso_values, int nV, int nF, int K, float* contours_merged,
+                               int32_t* contour_nums, void* workspace, size_t workspace_bytes,
+                               inf3dp_stream_t stream);
+/* Synchronises `stream` and reports data-dependent failures of the last call that used `workspace`
+ * (INF3DP_EOVERFLOW when the segment pool was too small).  seg_counts_host: optional host [K] array receiving
+ * the per-isovalue segment counts S_k (the reference's internal pairpoint_nums). */
+int inf3dp_extract_isocontours_status(const void* workspace, int K, int32_t* seg_counts_host,
+                                      inf3dp_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Three-field voxel intersection.  Replaces contour_cuda/ext.cpp:20-46 get_fields_intersection_inter_slice
+ * (-> intersection.cu:227-287, kernel :31-224).
+ *   slice/lattice1/lattice2 fields [Dx,Dy,Dz,8] f32 (corner expanded), iso arrays [Ns],[N1],[N2] f32,
+ *   voxel_centers [Dx,Dy,Dz,3] f32
+ *   -> inter_mask [Ns,N1,N2] u8 (0/1), isovalue_indices [Ns,N1,N2,3] i16 (-1 where unset),
+ *      intersections [Ns,N1,N2,3] f32.  All three fully written by the call.
+ * Deterministic: where several voxels hit one cell the LOWEST linear voxel index wins
+ * (the reference is last-writer-wins, i.e. any of them).
+ * ------------------------------------------------------------------------------------------------------- */
+size_t inf3dp_fields_intersection_workspace_bytes(int Dx, int Dy, int Dz, int Ns, int N1, int N2);
+int inf3dp_fields_intersection(const float* slice_fields, const float* lattice1_fields, const float* lattice2_fields,
+                               const float* slice_iso, const float* lattice1_iso, const float* lattice2_iso,
+                               const float* voxel_centers, int Dx, int Dy, int Dz, int Ns, int N1, int N2,
+                               uint8_t* inter_mask, int16_t* isovalue_indices, float* intersections,
+                               void* workspace, size_t workspace_bytes, inf3dp_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* INF3DP_H_ */

@@ -1,0 +1,121 @@
+// Shared host/device helpers of libinf3dp (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/inf3dp.h"
+
+namespace inf3dp {
+
+void set_error(const char* fmt, ...);
+
+#define INF3DP_CHECK_ARG(cond, ...)                      \
+    do {                                                 \
+        if (!(cond)) {                                   \
+            ::inf3dp::set_error(__VA_ARGS__);            \
+            return INF3DP_EINVAL;                        \
+        }                                                \
+    } while (0)
+
+#define INF3DP_CUDA(call)                                                                        \
+    do {                                                                                         \
+        cudaError_t e__ = (call);                                                                \
+        if (e__ != cudaSuccess) {                                                                \
+            ::inf3dp::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return INF3DP_ECUDA;                                                                 \
+        }                                                                                        \
+    } while (0)
+
+#define INF3DP_LAUNCH_CHECK(name)                                                                \
+    do {                                                                                         \
+        cudaError_t e__ = cudaGetLastError();                                                    \
+        if (e__ != cudaSuccess) {                                                                \
+            ::inf3dp::set_error("launch of %s failed: %s", name, cudaGetErrorString(e__));       \
+            return INF3DP_ECUDA;                                                                 \
+        }                                                                                        \
+    } while (0)
+
+inline int num_sms() {
+    static int cached[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        cached[dev] = n > 0 ? n : 148;
+    }
+    return cached[dev];
+}
+
+constexpr size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---------------------------------------------------------------------------------------------------------
+// Packed SIREN weights (built by inf3dp_siren_pack_weights, consumed by every engine).
+// ---------------------------------------------------------------------------------------------------------
+constexpr uint32_t kSirenMagic = 0x33445031u;  // "1PD3"
+constexpr int kHidden = 256;
+constexpr int kMaxOut = 64;
+constexpr int kMaxHiddenLayers = 16;
+
+struct SirenHeader {
+    uint32_t magic;
+    int in_features, hidden, num_hidden_layers, out_features, activation;
+    float omega0;
+    int tc_ok;             // flagship configuration: the tcgen05 engine may be used
+    uint64_t off_w0;       // f32 [hidden][4]   first layer, omega folded (sine), input padded to 4
+    uint64_t off_b0;       // f32 [hidden]
+    uint64_t off_wt;       // f32 [L][hidden k][hidden n]   hidden layers, transposed, omega folded
+    uint64_t off_b;        // f32 [L][hidden]
+    uint64_t off_wout;     // f32 [kMaxOut][hidden]  rows >= out_features are zero
+    uint64_t off_bout;     // f32 [kMaxOut]
+    uint64_t off_tc;       // tcgen05 operand images (see siren_tc.cu), 0 if !tc_ok
+    uint64_t total_bytes;
+    float tc_scale;        // power-of-two pre-scale applied to the FP16 hidden weights (undone in the epilogue)
+    float tc_inv_scale;
+    uint32_t pad[28];
+};
+static_assert(sizeof(SirenHeader) <= 256, "header must fit 256 bytes");
+
+struct SirenLayout {
+    size_t off_w0, off_b0, off_wt, off_b, off_wout, off_bout, off_tc, total;
+    bool tc_ok;
+};
+
+size_t siren_tc_section_bytes();  // siren_tc.cu
+
+inline bool siren_config_supported(int in_features, int hidden, int L, int out) {
+    return hidden == kHidden && (in_features == 3 || in_features == 4) && out >= 1 && out <= kMaxOut && L >= 0 &&
+           L <= kMaxHiddenLayers;
+}
+
+inline SirenLayout siren_layout(int in_features, int hidden, int L, int out, int activation) {
+    SirenLayout l{};
+    size_t o = 256;
+    l.off_w0 = o;   o += (size_t)hidden * 4 * 4;
+    l.off_b0 = o;   o += (size_t)hidden * 4;
+    l.off_wt = o;   o += (size_t)L * hidden * hidden * 4;
+    l.off_b = o;    o += (size_t)(L > 0 ? L : 1) * hidden * 4;
+    l.off_wout = o; o += (size_t)kMaxOut * hidden * 4;
+    l.off_bout = o; o += (size_t)kMaxOut * 4;
+    o = align_up(o, 1024);
+    l.tc_ok = (in_features == 3 && hidden == kHidden && L == 3 && out <= 8 && activation == INF3DP_ACT_SINE);
+    l.off_tc = o;
+    // the TC section is always reserved for in=3/L=3 so the blob size does not depend on the activation
+    if (in_features == 3 && hidden == kHidden && L == 3 && out <= 8) o += siren_tc_section_bytes();
+    l.total = align_up(o, 256);
+    return l;
+}
+
+// engine entry points (implemented in the respective .cu files)
+int siren_simt_launch(const void* packed, const SirenHeader& h, const float* x, int64_t n, int order, float* y,
+                      float* J, float* H, cudaStream_t stream);
+int siren_tc_launch(const void* packed, const SirenHeader& h, const float* x, int64_t n, int order, float* y,
+                    float* J, bool precise, cudaStream_t stream);
+int siren_tc_pack(const float* const* W, const float* const* b, float omega0, int out_features, void* packed,
+                  const SirenLayout& lay, SirenHeader& hdr, cudaStream_t stream);
+
+}  // namespace inf3dp

@@ -1,0 +1,30 @@
+"""inf3dp -- B200-native (sm_100a) implementation of INF-3DP's data-parallel hot path.
+
+Fused SIREN field queries (value / gradient / Hessian as forward-mode jets) and isocontour / field-intersection
+extraction, behind the reference's own Python surface.  See DESIGN.md and INTEGRATION.md at the repo root.
+"""
+from . import _lib
+from .siren import SingleBVPNet, MLPClassifier, set_engine, get_engine
+from .contours import extract_isocontours, get_fields_intersection_inter_slice, extract_isocontours_raw
+from .diffops import (gradient, hessian, hessian3d, jacobian, divergence, laplace, principal_curvatures,
+                      min_max_curvs_and_vectors)
+from .query import field_querying, field_query_with_grads, HostPipeline
+
+
+def patch_reference():
+    """Rebind the reference's hot-path classes in already-imported reference modules:
+    `modules.SingleBVPNet` -> inf3dp.SingleBVPNet.  `diff_operators` is left untouched: its autograd calls work on
+    the fused outputs."""
+    import sys
+    m = sys.modules.get("modules")
+    if m is not None:
+        m.SingleBVPNet = SingleBVPNet
+    return m is not None
+
+
+__all__ = [
+    "SingleBVPNet", "MLPClassifier", "set_engine", "get_engine", "extract_isocontours",
+    "get_fields_intersection_inter_slice", "extract_isocontours_raw", "gradient", "hessian", "hessian3d", "jacobian",
+    "divergence", "laplace", "principal_curvatures", "min_max_curvs_and_vectors", "field_querying",
+    "field_query_with_grads", "HostPipeline", "patch_reference",
+]

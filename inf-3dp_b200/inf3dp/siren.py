@@ -1,0 +1,239 @@
+"""Drop-in SIREN field network backed by the fused sm_100a jet kernels.
+
+Mirrors the reference surface (paths relative to the INF-3DP repository):
+  * modules.py:119-160  SingleBVPNet(out_features, type, in_features, mode, hidden_features, num_hidden_layers)
+                        forward({'coords': x}) -> {'model_in': x' (fresh leaf, requires_grad), 'model_out': y}
+  * modules.py:622-635  sine_init / first_layer_sine_init (same RNG call order => same weights for a given seed)
+  * state_dict keys     net.net.{i}.0.weight / .bias -- reference checkpoints load unchanged
+  * diff_operators.py   gradient / hessian / hessian3d keep working on the outputs: `model_out` is produced by a
+                        torch.autograd.Function whose backward contracts with the Jacobian computed by the same
+                        fused kernel (forward-mode, no autograd graph through the layers) and whose
+                        double-backward contracts with the Hessian from an order-2 launch.
+  * exp_scripts/train_levels.py:35-51  MLPClassifier (ReLU level MLP), same keys network.{0,2,4}.*
+
+Weights are constants for these kernels (inference); gradients flow to the coordinates only.
+There is no CPU path: CPU tensors raise, as the reference's CHECK_CUDA does for its native ops.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+
+import torch
+from torch import nn
+
+from . import _lib
+
+_JET_MODE = {"mode": "auto"}
+
+
+def set_engine(mode: str):
+    """Select the execution engine for all SIREN queries: 'auto' | 'simt' | 'tc_precise' | 'tc_fast'."""
+    if mode not in _lib.MODES:
+        raise ValueError(f"unknown engine {mode!r}; expected one of {sorted(_lib.MODES)}")
+    _JET_MODE["mode"] = mode
+
+
+def get_engine() -> str:
+    return _JET_MODE["mode"]
+
+
+class PackedWeights:
+    """Device blob produced by inf3dp_siren_pack_weights, re-packed when the source parameters change."""
+
+    def __init__(self, in_features, hidden, num_hidden_layers, out_features, activation, omega0=30.0):
+        self.cfg = (int(in_features), int(hidden), int(num_hidden_layers), int(out_features))
+        self.activation = activation
+        self.omega0 = float(omega0)
+        self.blob = None
+        self._sig = None
+
+    def _signature(self, weights, biases):
+        return tuple((t.data_ptr(), t._version, str(t.device)) for t in list(weights) + list(biases))
+
+    def get(self, weights, biases):
+        dev = weights[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("inf3dp: the SIREN kernels need CUDA tensors (no CPU fallback); call .cuda() on the model")
+        sig = self._signature(weights, biases)
+        if self.blob is not None and sig == self._sig:
+            return self.blob
+        L = _lib.lib()
+        nbytes = L.inf3dp_siren_packed_bytes(*self.cfg)
+        if nbytes == 0:
+            raise RuntimeError("inf3dp: unsupported network configuration in=%d hidden=%d hidden_layers=%d out=%d "
+                               "(supported: hidden 256, in 3 or 4, out 1..64)" % self.cfg)
+        ws = [w.detach().to(torch.float32).contiguous() for w in weights]
+        bs = [b.detach().to(torch.float32).contiguous() for b in biases]
+        n = len(ws)
+        wp = (ctypes.c_void_p * n)(*[w.data_ptr() for w in ws])
+        bp = (ctypes.c_void_p * n)(*[b.data_ptr() for b in bs])
+        blob = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(L.inf3dp_siren_pack_weights(wp, bp, *self.cfg, self.activation, self.omega0, _lib.ptr(blob),
+                                                   nbytes, _lib.stream_ptr(dev)))
+        self.blob, self._sig = blob, sig
+        return blob
+
+
+def jet(blob, x, order, out_features, mode=None):
+    """Raw fused query: x [n, in] (CUDA, f32) -> y [n,out], J [n,out,3] | None, H [n,out,3,3] | None."""
+    if not x.is_cuda:
+        raise RuntimeError("inf3dp: coords must be a CUDA tensor (no CPU fallback)")
+    x = x.detach().to(torch.float32).contiguous()
+    n = x.shape[0]
+    dev = x.device
+    y = torch.empty((n, out_features), dtype=torch.float32, device=dev)
+    J = torch.empty((n, out_features, 3), dtype=torch.float32, device=dev) if order >= 1 else None
+    H = torch.empty((n, out_features, 3, 3), dtype=torch.float32, device=dev) if order >= 2 else None
+    m = _lib.MODES[mode or _JET_MODE["mode"]]
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().inf3dp_siren_jet(_lib.ptr(blob), _lib.ptr(x), n, order, _lib.ptr(y), _lib.ptr(J),
+                                               _lib.ptr(H), m, _lib.stream_ptr(dev)))
+    return y, J, H
+
+
+class _SirenJacobian(torch.autograd.Function):
+    """J(x) as a differentiable node: its backward contracts with the Hessian of an order-2 launch."""
+
+    @staticmethod
+    def forward(ctx, x, net, J_pre):
+        ctx.net = net
+        ctx.save_for_backward(x)
+        if J_pre is not None:
+            return J_pre.view(*x.shape[:-1], net.out_features, 3)
+        _, J, _ = net._jet(x.reshape(-1, x.shape[-1]), 1)
+        return J.view(*x.shape[:-1], net.out_features, 3)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gJ):
+        (x,) = ctx.saved_tensors
+        net = ctx.net
+        _, _, H = net._jet(x.reshape(-1, x.shape[-1]), 2)
+        g = torch.einsum("noi,noik->nk", gJ.reshape(-1, net.out_features, 3).to(H.dtype), H)
+        return g.view_as(x), None, None
+
+
+class _SirenValue(torch.autograd.Function):
+    """y(x); backward = grad_out . J with J from the fused forward-mode kernel (twice differentiable)."""
+
+    @staticmethod
+    def forward(ctx, x, net, eager):
+        ctx.net = net
+        flat = x.reshape(-1, x.shape[-1])
+        if eager:
+            y, J, _ = net._jet(flat, 1)
+        else:
+            y, _, _ = net._jet(flat, 0)
+            J = None
+        ctx.save_for_backward(x, J) if J is not None else ctx.save_for_backward(x)
+        ctx.has_J = J is not None
+        return y.view(*x.shape[:-1], net.out_features)
+
+    @staticmethod
+    def backward(ctx, gy):
+        if not ctx.needs_input_grad[0]:
+            return None, None, None
+        saved = ctx.saved_tensors
+        x = saved[0]
+        J_pre = saved[1] if ctx.has_J else None
+        J = _SirenJacobian.apply(x, ctx.net, J_pre)
+        gx = (gy.unsqueeze(-1) * J).sum(-2)
+        return gx, None, None
+
+
+class FusedSirenMixin:
+    """Shared query plumbing of the drop-in modules (expects .out_features, ._packed, ._weights())."""
+
+    lazy_jacobian = False  # True: forward computes values only and the Jacobian is launched on demand in backward
+
+    def _jet(self, flat_x, order, mode=None):
+        ws, bs = self._weights()
+        blob = self._packed.get(ws, bs)
+        return jet(blob, flat_x, order, self.out_features, mode)
+
+    @torch.no_grad()
+    def query(self, coords, order=1, mode=None):
+        """Fused value / Jacobian / Hessian query without autograd bookkeeping.
+
+        coords [..., in] -> (y [..., out], J [..., out, 3] or None, H [..., out, 3, 3] or None)."""
+        flat = coords.reshape(-1, coords.shape[-1])
+        y, J, H = self._jet(flat, order, mode)
+        lead = coords.shape[:-1]
+        y = y.view(*lead, self.out_features)
+        if J is not None:
+            J = J.view(*lead, self.out_features, 3)
+        if H is not None:
+            H = H.view(*lead, self.out_features, 3, 3)
+        return y, J, H
+
+
+class SingleBVPNet(FusedSirenMixin, nn.Module):
+    """Drop-in for modules.SingleBVPNet (modules.py:119-166), mode='mlp', type in {'sine','relu'}."""
+
+    def __init__(self, out_features=1, type="sine", in_features=2, mode="mlp", hidden_features=256,
+                 num_hidden_layers=3, **kwargs):
+        super().__init__()
+        if mode != "mlp":
+            raise NotImplementedError("inf3dp.SingleBVPNet: only mode='mlp' is on the accelerated path "
+                                      "(rbf / nerf encodings are unused by INF-3DP, SURVEY.md section 2 #13)")
+        if type not in ("sine", "relu"):
+            raise NotImplementedError(f"inf3dp.SingleBVPNet: nonlinearity {type!r} is not on the accelerated path")
+        self.mode = mode
+        self.type = type
+        self.in_features, self.out_features = int(in_features), int(out_features)
+        self.hidden_features, self.num_hidden_layers = int(hidden_features), int(num_hidden_layers)
+        # module tree chosen so that state_dict keys equal the reference's: net.net.{i}.0.{weight,bias}
+        dims = [in_features] + [hidden_features] * (num_hidden_layers + 1) + [out_features]
+        layers = [nn.Sequential(nn.Linear(dims[i], dims[i + 1])) for i in range(len(dims) - 1)]
+        holder = nn.Module()
+        holder.net = nn.Sequential(*layers)
+        self.net = holder
+        # same RNG call order as FCBlock.__init__ (modules.py:66-87): default nn.Linear init per layer, then the
+        # nonlinearity's init over all layers, then the first-layer init
+        with torch.no_grad():
+            if type == "sine":
+                for seq in layers:  # sine_init, modules.py:622-627
+                    w = seq[0].weight
+                    bound = math.sqrt(6 / w.size(-1)) / 30
+                    w.uniform_(-bound, bound)
+                w0 = layers[0][0].weight  # first_layer_sine_init, modules.py:630-635
+                w0.uniform_(-1 / w0.size(-1), 1 / w0.size(-1))
+            else:
+                for seq in layers:  # init_weights_normal, modules.py:589-593
+                    nn.init.kaiming_normal_(seq[0].weight, a=0.0, nonlinearity="relu", mode="fan_in")
+        act = _lib.ACT_SINE if type == "sine" else _lib.ACT_RELU
+        self._packed = PackedWeights(in_features, hidden_features, num_hidden_layers, out_features, act, 30.0)
+
+    def _weights(self):
+        lins = [seq[0] for seq in self.net.net]
+        return [l.weight for l in lins], [l.bias for l in lins]
+
+    def forward(self, model_input, params=None):
+        if params is not None:
+            raise NotImplementedError("inf3dp.SingleBVPNet: hypernetwork `params` are not supported (inference path)")
+        coords_org = model_input["coords"].clone().detach().requires_grad_(True)  # modules.py:148
+        eager = torch.is_grad_enabled() and not self.lazy_jacobian
+        out = _SirenValue.apply(coords_org, self, eager)
+        return {"model_in": coords_org, "model_out": out}
+
+
+class MLPClassifier(FusedSirenMixin, nn.Module):
+    """Drop-in for exp_scripts/train_levels.py:35-51 (4 -> 256 -> 256 -> C ReLU logits), keys network.{0,2,4}.*"""
+
+    def __init__(self, input_dim=4, hidden_dim=256, num_classes=3):
+        super().__init__()
+        self.network = nn.Sequential(nn.Linear(input_dim, hidden_dim), nn.ReLU(), nn.Linear(hidden_dim, hidden_dim),
+                                     nn.ReLU(), nn.Linear(hidden_dim, num_classes))
+        self.out_features = int(num_classes)
+        self._packed = PackedWeights(input_dim, hidden_dim, 1, num_classes, _lib.ACT_RELU, 1.0)
+
+    def _weights(self):
+        lins = [self.network[0], self.network[2], self.network[4]]
+        return [l.weight for l in lins], [l.bias for l in lins]
+
+    def forward(self, x):
+        flat = x.reshape(-1, x.shape[-1])
+        y, _, _ = self._jet(flat, 0)
+        return y.view(*x.shape[:-1], self.out_features)

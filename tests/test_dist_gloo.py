@@ -1,0 +1,38 @@
+"""CPU: the N>1 sharding / all-gather path on the gloo backend, world_size 2."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT
+
+
+def _worker(rank, world, port, n):
+    sys.path.insert(0, os.path.join(ROOT, "inf-3dp_b200"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from inf3dp.dist import all_gather_rows, shard_range
+    full = torch.arange(n * 4, dtype=torch.float32).view(n, 4)
+    lo, hi, per = shard_range(n, rank, world)
+    got = all_gather_rows(full[lo:hi].clone(), n)
+    assert torch.equal(got, full), (rank, got.shape)
+    cnt = all_gather_rows(torch.arange(lo, hi, dtype=torch.int32), n)
+    assert torch.equal(cnt, torch.arange(n, dtype=torch.int32))
+    dist.destroy_process_group()
+
+
+def test_shard_ranges_cover_exactly():
+    from inf3dp.dist import shard_range
+    for n in (0, 1, 7, 200, 16777216):
+        for w in (1, 2, 4, 8):
+            spans = [shard_range(n, r, w)[:2] for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+
+
+def test_all_gather_rows_world2():
+    for n in (7, 8):
+        mp.spawn(_worker, args=(2, 29533 + n, n), nprocs=2, join=True)

@@ -1,0 +1,166 @@
+"""GPU parity tests (through the C ABI) for the fused SIREN jet: CUDA path vs the numpy oracle (fp64) and the
+golden vectors recorded from the reference.  Tolerances are the north_star ones, written out here:
+    |df| <= 1e-4 * bbox diagonal (3.46e-4 for [-1,1]^3), gradient angle <= 0.1 degrees.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import layers_from_golden
+from oracle import siren_oracle as so
+
+pytestmark = pytest.mark.gpu
+
+TOL_F = 1e-4 * np.sqrt(12.0)
+TOL_ANGLE = 0.1
+
+
+def _net(golden, name="sdf", out=1):
+    import inf3dp
+    net = inf3dp.SingleBVPNet(type="sine", in_features=3, out_features=out)
+    sd = {k[len(name) + 1:]: torch.from_numpy(np.asarray(golden[k])) for k in golden.files if k.startswith(name + "/net.")}
+    net.load_state_dict(sd)
+    return net.cuda()
+
+
+ENGINES = ["simt", "tc_precise"]
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_value_gradient_vs_reference_golden(golden, engine):
+    net = _net(golden)
+    x = torch.from_numpy(golden["x"]).cuda()
+    y, J, _ = net.query(x, order=1, mode=engine)
+    y, J = y.cpu().numpy(), J.cpu().numpy()
+    assert np.abs(y - golden["sdf/y"]).max() <= TOL_F
+    assert so.angle_deg(J[:, 0], golden["sdf/grad"]).max() <= TOL_ANGLE
+    # and against the fp64 oracle (the reference's own fp32 error is ~1e-7 / 0.007 deg)
+    yo, Jo, _ = so.siren_jet(layers_from_golden(golden, "sdf"), golden["x"].astype(np.float64), order=1)
+    assert np.abs(y - yo).max() <= TOL_F
+    assert so.angle_deg(J[:, 0], Jo[:, 0]).max() <= TOL_ANGLE
+    if engine == "simt":  # the FP32 engine is as accurate as the reference itself
+        assert np.abs(y - yo).max() < 5e-6
+        assert so.angle_deg(J[:, 0], Jo[:, 0]).max() < 0.02
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_value_only_and_quaternion_out4(golden, engine):
+    net = _net(golden, "quat", 4)
+    x = torch.from_numpy(golden["x"]).cuda()
+    y0, J0, _ = net.query(x, order=0, mode=engine)
+    assert J0 is None and np.abs(y0.cpu().numpy() - golden["quat/y"]).max() <= TOL_F
+    y1, J1, _ = net.query(x, order=1, mode=engine)
+    assert np.abs(y1.cpu().numpy() - golden["quat/y"]).max() <= TOL_F
+    Jr = golden["quat/jac"]
+    for c in range(4):
+        assert so.angle_deg(J1.cpu().numpy()[:, c], Jr[:, c]).max() <= TOL_ANGLE
+
+
+def test_hessian_and_curvature_vs_reference(golden):
+    import inf3dp
+    net = _net(golden)
+    x = torch.from_numpy(golden["sdf/hess_x"]).cuda()
+    y, J, H = net.query(x, order=2, mode="simt")
+    Hn = H.cpu().numpy()
+    ref = golden["sdf/hess3d"]
+    rel = np.linalg.norm((Hn - ref).reshape(len(Hn), -1), axis=1) / np.linalg.norm(ref.reshape(len(ref), -1), axis=1)
+    assert rel.max() <= 1e-3  # proposed tolerance; fp32-vs-fp64 floor of the reference: 1.5e-5
+    assert np.array_equal(Hn, np.swapaxes(Hn, -1, -2))
+    kap, dirs = inf3dp.principal_curvatures(J[:64, 0], H[:64, 0])
+    kr, dr = golden["sdf/curv_kappa"], golden["sdf/curv_dirs"]
+    kap, dirs = kap.cpu().numpy(), dirs.cpu().numpy()
+    assert np.abs(kap - kr).max() <= 2e-2 * max(1.0, np.abs(kr).max())
+    sep = np.abs(kr[:, 1] - kr[:, 0]) > 1e-2 * np.abs(kr).max()
+    assert (np.abs((dirs * dr).sum(-1))[sep] > np.cos(np.radians(0.5))).all()
+
+
+def test_reference_call_pattern_autograd(golden):
+    """forward({'coords'}) -> dict; diff_operators.gradient / hessian3d / hessian on it (modules.py:143-160,
+    diff_operators.py:6-44,128-132), for [N,3] and [1,N,3]."""
+    import inf3dp
+    net = _net(golden)
+    x = torch.from_numpy(golden["x"][:256]).cuda()
+    out = net({"coords": x})
+    assert out["model_in"].requires_grad and out["model_in"].is_leaf and out["model_out"].shape == (256, 1)
+    g = inf3dp.gradient(out["model_out"], out["model_in"])
+    assert so.angle_deg(g.detach().cpu().numpy(), golden["sdf/grad"][:256]).max() <= TOL_ANGLE
+    # the stock autograd formulation of the reference (no fused shortcut): grad of grad
+    gy = torch.ones_like(out["model_out"][..., 0])
+    dydx = torch.autograd.grad(out["model_out"][..., 0], out["model_in"], gy, create_graph=True)[0]
+    row0 = torch.autograd.grad(dydx[..., 0], out["model_in"], gy, create_graph=True)[0]
+    xs = torch.from_numpy(golden["sdf/hess_x"]).cuda()
+    o2 = net({"coords": xs})
+    h = inf3dp.hessian3d(o2["model_out"], o2["model_in"]).cpu().numpy()
+    ref = golden["sdf/hess3d"]
+    assert np.abs(h - ref).max() <= 1e-3 * np.abs(ref).max()
+    dydx2 = torch.autograd.grad(o2["model_out"][..., 0], o2["model_in"], torch.ones_like(o2["model_out"][..., 0]), create_graph=True)[0]
+    r0 = torch.autograd.grad(dydx2[..., 0], o2["model_in"], torch.ones_like(dydx2[..., 0]), create_graph=True)[0]
+    assert np.abs(r0.detach().cpu().numpy() - ref[:, 0, 0, :]).max() <= 1e-3 * np.abs(ref).max()
+    assert row0.shape == (256, 3)
+    ob = net({"coords": xs[None]})
+    assert ob["model_out"].shape == (1, len(xs), 1)
+    hb, status = inf3dp.hessian(ob["model_out"], ob["model_in"])
+    assert status == 0 and np.abs(hb.cpu().numpy()[0] - ref).max() <= 1e-3 * np.abs(ref).max()
+    gb = inf3dp.gradient(ob["model_out"], ob["model_in"])
+    assert gb.shape == (1, len(xs), 3)
+    # custom grad_outputs (diff_operators.py:129-131)
+    go = torch.full_like(out["model_out"], 2.0)
+    g2 = inf3dp.gradient(out["model_out"], out["model_in"], go)
+    assert torch.allclose(g2, 2 * g, rtol=1e-6, atol=1e-8)
+
+
+def test_level_mlp_relu(golden):
+    import inf3dp
+    lvl = inf3dp.MLPClassifier(num_classes=8)
+    lvl.load_state_dict({k[len("level/"):]: torch.from_numpy(np.asarray(golden[k])) for k in golden.files if k.startswith("level/network")})
+    lvl.cuda()
+    lo = lvl(torch.from_numpy(golden["level/x"]).cuda()).cpu().numpy()
+    assert np.abs(lo - golden["level/logits"]).max() < 1e-5
+    assert np.array_equal(lo.argmax(-1), golden["level/logits"].argmax(-1))
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("n", [0, 1, 31, 32, 33, 1000, 4097])
+def test_ragged_sizes_and_batch_split_invariance(golden, engine, n):
+    net = _net(golden)
+    g = torch.Generator().manual_seed(n)
+    x = (torch.rand(n, 3, generator=g) * 2 - 1).cuda()
+    y, J, _ = net.query(x, order=1, mode=engine)
+    assert y.shape == (n, 1) and J.shape == (n, 1, 3)
+    if n == 0:
+        return
+    yo, Jo, _ = so.siren_jet(layers_from_golden(golden, "sdf"), x.cpu().numpy().astype(np.float64), order=1)
+    assert np.abs(y.cpu().numpy() - yo).max() <= TOL_F
+    assert so.angle_deg(J.cpu().numpy()[:, 0], Jo[:, 0]).max() <= TOL_ANGLE
+    if n > 40:  # a point's result does not depend on its position in the batch
+        k = 37
+        y2, J2, _ = net.query(x[k:], order=1, mode=engine)
+        assert torch.equal(y2, y[k:]) and torch.equal(J2, J[k:])
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_million_points_size_independent_properties(golden, engine):
+    """Full-size property check (no oracle at this size): determinism, batch-split invariance, and agreement
+    between engines on a sample checked against the oracle."""
+    net = _net(golden)
+    n = 1 << 20
+    g = torch.Generator().manual_seed(0)
+    x = (torch.rand(n, 3, generator=g) * 2 - 1).cuda()
+    y, J, _ = net.query(x, order=1, mode=engine)
+    ya, Ja, _ = net.query(x, order=1, mode=engine)
+    assert torch.equal(y, ya) and torch.equal(J, Ja)
+    assert torch.isfinite(y).all() and torch.isfinite(J).all()
+    idx = torch.randperm(n, generator=g)[:4096]
+    yo, Jo, _ = so.siren_jet(layers_from_golden(golden, "sdf"), x[idx.cuda()].cpu().numpy().astype(np.float64), order=1)
+    assert np.abs(y[idx.cuda()].cpu().numpy() - yo).max() <= TOL_F
+    assert so.angle_deg(J[idx.cuda()].cpu().numpy()[:, 0], Jo[:, 0]).max() <= TOL_ANGLE
+
+
+def test_weights_repack_after_update(golden):
+    net = _net(golden)
+    x = torch.from_numpy(golden["x"][:64]).cuda()
+    y0, _, _ = net.query(x, order=0, mode="simt")
+    with torch.no_grad():
+        net.net.net[4][0].bias.add_(1.0)
+    y1, _, _ = net.query(x, order=0, mode="simt")
+    assert torch.allclose(y1, y0 + 1.0, atol=1e-6)
