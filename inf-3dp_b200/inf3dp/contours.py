@@ -43,7 +43,7 @@ def extract_isocontours_raw(vertices, faces, fields, iso_values, sync=True, want
     merged = torch.empty((K, nF, 3), dtype=torch.float32, device=dev)
     nums = torch.empty((K,), dtype=torch.int32, device=dev)
     if K == 0:
-        return (merged, nums, None) if want_seg_counts else (merged, nums)
+        return (merged, nums, torch.zeros(0, dtype=torch.int32)) if want_seg_counts else (merged, nums)
     ws_bytes = L.inf3dp_extract_isocontours_workspace_bytes(nV, nF, K)
     seg_host = (ctypes.c_int32 * K)() if want_seg_counts else None
     with torch.cuda.device(dev):
