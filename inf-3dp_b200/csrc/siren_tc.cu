@@ -1,19 +1,557 @@
-// tcgen05 tensor-core engine of the fused SIREN jet -- placeholder until the kernel lands (next commit).
+// tcgen05 tensor-core engine of the fused SIREN jet (sm_100a): value or value+gradient of the flagship network
+// 3 -> 256 -> 256 -> 256 -> 256 -> out (sine, out <= 8) in ONE persistent kernel, activations never leave the SM.
+//
+// Replaces modules.py:143-160 (forward) + diff_operators.py:128-132 (gradient via autograd) of the reference.
+//
+// Formulation (forward-mode jet).  A CTA owns 128 "rows" at a time:
+//   ORDER 1: 32 points x 4 jet columns, row r = 4*p + c  (c = 0 value, 1..3 = d/dx, d/dy, d/dz)
+//   ORDER 0: 128 points, row r = p
+// A hidden layer is one 128 x 256 x 256 GEMM  D[r, n] = sum_k A[r, k] * W'[n, k]  on the 5th-gen tensor cores:
+//   * A (activations) lives in TENSOR MEMORY and is consumed from there (tcgen05.mma, A-from-TMEM form),
+//     B (weights, FP16 UMMA K-major core-matrix images prepared at pack time) streams L2 -> shared memory through
+//     a 6-stage cp.async.bulk / mbarrier ring, D accumulates in FP32 in the other half of tensor memory.
+//   * PRECISE mode splits both operands into FP16 hi + lo and issues three MMAs per K-step
+//     (a_hi*W_hi + a_lo*W_hi + a_hi*W_lo): FP32-class accuracy (measured need, SURVEY.md section 7 hard part 1);
+//     FAST mode issues a_hi*W_hi only.
+//   * The epilogue warps read D with tcgen05.ld, apply the jet update
+//         value row:   a  = sin(z + b)            tangent row: da = cos(z_value + b) * dz
+//     (the tangent lanes fetch their point's z with one quad shuffle and evaluate cos as sin(. + pi/2), so all 32
+//     lanes run one MUFU.SIN per feature), split to FP16 hi/lo and write the next layer's A operand with tcgen05.st
+//     IN PLACE over the accumulator columns they just consumed.  The two halves of tensor memory swap roles every
+//     layer; the loop over K is the outer MMA loop (N = 256 per instruction), so the MMAs of layer l+1 start as
+//     soon as the first 32-feature slice of layer l's activations is written and overlap the rest of the epilogue.
+//   * Layer 0 (3 -> 256) and the omega0 folding are FP32 CUDA-core work (north_star), the output layer is a
+//     128 x 16 x 256 MMA.
+// Warp roles (320 threads): warps 0-7 epilogue (two warps per TMEM lane quadrant, interleaved 32-column slices),
+// warp 8 weight producer (one elected lane), warp 9 TMEM allocator + MMA issuer (one elected lane).
+// Every mbarrier wait carries a watchdog that traps instead of hanging the GPU.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace inf3dp {
 
-size_t siren_tc_section_bytes() { return 0; }
+namespace {
 
-int siren_tc_pack(const float* const*, const float* const*, float, int, void*, const SirenLayout&, SirenHeader& hdr,
-                  cudaStream_t) {
-    hdr.tc_ok = 0;
+// ---- packed TC section layout (offsets relative to SirenHeader::off_tc) -----------------------------------
+constexpr size_t kTcOffScales = 0;        // float inv_scale[4]: hidden layers 1..3, output layer
+constexpr size_t kTcOffB4 = 64;           // float b4[8]
+constexpr size_t kTcOffMaxAbs = 128;      // uint32 max |w| bits per layer [4] (pack-time scratch)
+constexpr size_t kTcOffBias = 256;        // float bias_phase[3][256][2] = (b', b' + pi/2)
+constexpr size_t kTcOffOutImg = 7168;     // out-layer image: 16 K-steps x 512 B hi, then lo  (16 KB)
+constexpr size_t kTcOffHidImg = 7168 + 16384;  // 3 layers x 8 stages x 32 KB
+constexpr size_t kStageBytes = 32768;     // 2 K-steps x (hi 8 KB) then 2 K-steps x (lo 8 KB)
+constexpr size_t kLayerImgBytes = 8 * kStageBytes;
+constexpr size_t kTcSectionBytes = kTcOffHidImg + 3 * kLayerImgBytes;
+
+// ---- shared memory layout -----------------------------------------------------------------------------------
+constexpr int kStages = 6;
+constexpr uint32_t kSmemRing = 0;
+constexpr uint32_t kSmemOutImg = kStages * kStageBytes;              // 196608
+constexpr uint32_t kSmemBias = kSmemOutImg + 16384;                  // 212992
+constexpr uint32_t kSmemW0 = kSmemBias + 6144;                       // 219136
+constexpr uint32_t kSmemB0 = kSmemW0 + 4096;                         // 223232
+constexpr uint32_t kSmemMisc = kSmemB0 + 1024;                       // 224256: inv_scale[4], b4[8]
+constexpr uint32_t kSmemBars = kSmemMisc + 64;                       // 224320
+constexpr int kBarWFull = 0, kBarWEmpty = kStages, kBarAReady = 2 * kStages, kBarDFull = 2 * kStages + 8,
+              kBarOutImg = 2 * kStages + 9, kNumBars = 2 * kStages + 10;
+constexpr uint32_t kSmemTmemPtr = kSmemBars + kNumBars * 8;
+constexpr uint32_t kSmemTotal = kSmemTmemPtr + 16;
+static_assert(kSmemTotal <= 232448 - 1024, "shared memory budget (1 KB reserved for base alignment)");
+
+constexpr int kThreadsTc = 320;
+constexpr float kHalfPi = 1.57079632679489662f;
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" ::"r"(bar), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Wait with a watchdog: a protocol bug traps (launch failure) instead of hanging the device.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000ll) {
+            printf("inf3dp siren_tc: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x,
+                   threadIdx.x, bar, parity);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem descriptor]   (kind::f16, FP32 accumulate)
+__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}"
+                 ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+// K-major, no-swizzle UMMA shared-memory descriptor: core matrix = 8 rows x 16 bytes (128 contiguous bytes);
+// LBO = byte stride between the two K-halves of a K=16 step, SBO = byte stride between 8-row groups.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+    return d;                // base_offset 0, lbo_mode 0, layout_type SWIZZLE_NONE
+}
+// instruction descriptor: D=F32, A=B=F16, both K-major, M=128, N as given
+__host__ __device__ constexpr uint32_t make_idesc(int n) {
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+#define TC_LD32(addr, v)                                                                                         \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                       \
+                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,"  \
+                 "%26,%27,%28,%29,%30,%31}, [%32];"                                                              \
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),  \
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),       \
+                   "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),     \
+                   "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),     \
+                   "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                                                         \
+                 : "r"(addr) : "memory")
+
+#define TC_ST32(addr, v)                                                                                         \
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "                                                 \
+                 "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,"  \
+                 "%27,%28,%29,%30,%31,%32};"                                                                     \
+                 ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]),        \
+                   "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]),   \
+                   "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), \
+                   "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), \
+                   "r"(v[31]) : "memory")
+
+#define TC_ST16(addr, v)                                                                                         \
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "                                                 \
+                 "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"                                      \
+                 ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]),        \
+                   "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]),   \
+                   "r"(v[15]) : "memory")
+
+#define TC_LD16(addr, v)                                                                                         \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "                                                       \
+                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"                                \
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),  \
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),       \
+                   "=r"(v[15])                                                                                   \
+                 : "r"(addr) : "memory")
+
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float sin_mufu(float x) {
+    float r;
+    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+// FP32 argument reduction to [-pi, pi] (two-constant Cody-Waite), then MUFU: used for layer 0 where |z| reaches ~50.
+__device__ __forceinline__ float sin_reduced(float x) {
+    const float k = rintf(x * 0.15915494309189535f);
+    float r = fmaf(-k, 6.28318548202514648f, x);        // 2*pi rounded to FP32
+    r = fmaf(-k, -1.74845553146951715e-7f, r);           // 2*pi - fl(2*pi)
+    return sin_mufu(r);
+}
+
+// Split two FP32 values into packed FP16 hi and lo words (value 0 in the low half = lower feature index).
+template <bool PRECISE>
+__device__ __forceinline__ void split_pack(float o0, float o1, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(o0, o1);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    if (PRECISE) {
+        const float2 hf = __half22float2(h);
+        const __half2 l = __floats2half2_rn(o0 - hf.x, o1 - hf.y);
+        lo = *reinterpret_cast<const uint32_t*>(&l);
+    } else {
+        lo = 0u;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+template <int ORDER, bool PRECISE>
+__global__ void __launch_bounds__(kThreadsTc, 1)
+siren_tc_kernel(const char* __restrict__ packed, SirenHeader h, const float* __restrict__ x, int64_t n,
+                float* __restrict__ y, float* __restrict__ J) {
+    extern __shared__ unsigned char smem_dyn[];
+    // 1 KB alignment for the bulk-copy destinations / UMMA operands
+    const uint32_t sbase = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+    unsigned char* sptr = smem_dyn + (sbase - smem_u32(smem_dyn));
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const char* tc = packed + h.off_tc;
+
+    constexpr int kPts = ORDER == 1 ? 32 : 128;   // points per tile
+    const int out_f = h.out_features;
+    const int64_t num_tiles = (n + kPts - 1) / kPts;
+    const int my_tiles = (int)((num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);  // blockIdx.x < num_tiles
+
+    const uint32_t bars = sbase + kSmemBars;
+    auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
+
+    // ---- one-time setup --------------------------------------------------------------------------------------
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(bar(kBarWFull + s), 1); mbar_init(bar(kBarWEmpty + s), 1); }
+        for (int m = 0; m < 8; ++m) mbar_init(bar(kBarAReady + m), 4);
+        mbar_init(bar(kBarDFull), 1);
+        mbar_init(bar(kBarOutImg), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    {   // small FP32 tables through the generic proxy (read by CUDA cores only)
+        float* s_bias = reinterpret_cast<float*>(sptr + kSmemBias);
+        const float* g_bias = reinterpret_cast<const float*>(tc + kTcOffBias);
+        for (int i = tid; i < 3 * 256 * 2; i += kThreadsTc) s_bias[i] = g_bias[i];
+        float* s_w0 = reinterpret_cast<float*>(sptr + kSmemW0);
+        const float* g_w0 = reinterpret_cast<const float*>(packed + h.off_w0);
+        for (int i = tid; i < 256 * 4; i += kThreadsTc) s_w0[i] = g_w0[i];
+        float* s_b0 = reinterpret_cast<float*>(sptr + kSmemB0);
+        const float* g_b0 = reinterpret_cast<const float*>(packed + h.off_b0);
+        for (int i = tid; i < 256; i += kThreadsTc) s_b0[i] = g_b0[i];
+        float* s_misc = reinterpret_cast<float*>(sptr + kSmemMisc);
+        if (tid < 4) s_misc[tid] = reinterpret_cast<const float*>(tc + kTcOffScales)[tid];
+        if (tid >= 4 && tid < 12) s_misc[tid] = reinterpret_cast<const float*>(tc + kTcOffB4)[tid - 4];
+    }
+    if (warp == 9) {  // TMEM: all 512 columns (one CTA per SM by construction: ~219 KB of shared memory)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(sbase + kSmemTmemPtr), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sptr + kSmemTmemPtr);
+    const uint32_t regionP = tmem, regionQ = tmem + 256;
+
+    if (warp == 8) {
+        // ================= weight producer =====================================================================
+        if (lane == 0) {
+            mbar_expect_tx(bar(kBarOutImg), 16384);
+            bulk_g2s(sbase + kSmemOutImg, tc + kTcOffOutImg, 16384, bar(kBarOutImg));
+            const uint32_t copy_bytes = PRECISE ? (uint32_t)kStageBytes : (uint32_t)(kStageBytes / 2);
+            uint32_t stage = 0, phase = 0;
+            for (int it = 0; it < my_tiles; ++it) {
+                for (int l = 0; l < 3; ++l) {
+                    const char* img = tc + kTcOffHidImg + (size_t)l * kLayerImgBytes;
+                    for (int s = 0; s < 8; ++s) {
+                        mbar_wait(bar(kBarWEmpty + stage), phase ^ 1u);
+                        mbar_expect_tx(bar(kBarWFull + stage), copy_bytes);
+                        bulk_g2s(sbase + kSmemRing + stage * (uint32_t)kStageBytes, img + (size_t)s * kStageBytes,
+                                 copy_bytes, bar(kBarWFull + stage));
+                        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 9) {
+        // ================= MMA issuer ===========================================================================
+        if (lane == 0) {
+            constexpr uint32_t idesc256 = make_idesc(256);
+            constexpr uint32_t idesc16 = make_idesc(16);
+            uint32_t stage = 0, wphase = 0;
+            uint32_t aphase = 0;  // parity of the a_ready barriers (one completion per activation version)
+            mbar_wait(bar(kBarOutImg), 0);
+            for (int it = 0; it < my_tiles; ++it) {
+                // hidden layers 1..3: A alternates P,Q,P ; D alternates Q,P,Q
+                for (int l = 0; l < 3; ++l) {
+                    const uint32_t regA = (l & 1) ? regionQ : regionP;
+                    const uint32_t regD = (l & 1) ? regionP : regionQ;
+                    for (int t = 0; t < 16; ++t) {
+                        if ((t & 1) == 0) {
+                            mbar_wait(bar(kBarAReady + (t >> 1)), aphase);
+                            mbar_wait(bar(kBarWFull + stage), wphase);
+                            tc_fence_after();
+                        }
+                        const uint32_t sb = sbase + kSmemRing + stage * (uint32_t)kStageBytes + (uint32_t)(t & 1) * 8192u;
+                        const uint64_t bh = make_desc(sb, 4096, 128);
+                        const uint32_t a_hi = regA + 32u * (uint32_t)(t >> 1) + 8u * (uint32_t)(t & 1);
+                        mma_ts(regD, a_hi, bh, idesc256, t > 0 ? 1u : 0u);
+                        if (PRECISE) {
+                            const uint64_t bl = make_desc(sb + 16384u, 4096, 128);
+                            mma_ts(regD, a_hi + 16u, bh, idesc256, 1u);
+                            mma_ts(regD, a_hi, bl, idesc256, 1u);
+                        }
+                        if (t & 1) {
+                            tc_commit(bar(kBarWEmpty + stage));  // stage free once these MMAs have read it
+                            if (++stage == kStages) { stage = 0; wphase ^= 1u; }
+                        }
+                    }
+                    tc_commit(bar(kBarDFull));
+                    aphase ^= 1u;
+                }
+                // output layer: A = activations of layer 3 (region Q), D = region P columns [0,16)
+                for (int t = 0; t < 16; ++t) {
+                    if ((t & 1) == 0) {
+                        mbar_wait(bar(kBarAReady + (t >> 1)), aphase);
+                        tc_fence_after();
+                    }
+                    const uint32_t sb = sbase + kSmemOutImg + (uint32_t)t * 512u;
+                    const uint64_t bh = make_desc(sb, 256, 128);
+                    const uint32_t a_hi = regionQ + 32u * (uint32_t)(t >> 1) + 8u * (uint32_t)(t & 1);
+                    mma_ts(regionP, a_hi, bh, idesc16, t > 0 ? 1u : 0u);
+                    if (PRECISE) {
+                        const uint64_t bl = make_desc(sb + 8192u, 256, 128);
+                        mma_ts(regionP, a_hi + 16u, bh, idesc16, 1u);
+                        mma_ts(regionP, a_hi, bl, idesc16, 1u);
+                    }
+                }
+                tc_commit(bar(kBarDFull));
+                aphase ^= 1u;
+            }
+        }
+    } else {
+        // ================= epilogue warps 0..7 ===================================================================
+        const int quad = warp & 3;           // TMEM lane quadrant this warp may access
+        const int grp = warp >> 2;           // 0: slices 0,2,4,6   1: slices 1,3,5,7
+        const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+        const int row = quad * 32 + lane;    // TMEM lane = tile row
+        const int c = ORDER == 1 ? (lane & 3) : 0;          // jet column of this row
+        const int p_local = ORDER == 1 ? (row >> 2) : row;  // point within the tile
+        const int qbase = lane & ~3;                         // lane holding this point's value row
+        const float* s_bias = reinterpret_cast<const float*>(sptr + kSmemBias) + (c != 0 ? 1 : 0);
+        const float4* s_w0 = reinterpret_cast<const float4*>(sptr + kSmemW0);
+        const float* s_b0 = reinterpret_cast<const float*>(sptr + kSmemB0);
+        const float* s_misc = reinterpret_cast<const float*>(sptr + kSmemMisc);
+        const float phase0 = c != 0 ? kHalfPi : 0.f;
+        uint32_t dphase = 0;
+
+        for (int it = 0; it < my_tiles; ++it) {
+            const int64_t tile = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
+            const int64_t pt = tile * kPts + p_local;
+            const bool pvalid = pt < n;
+            float px = 0.f, py = 0.f, pz = 0.f;
+            if (pvalid) { px = x[3 * pt]; py = x[3 * pt + 1]; pz = x[3 * pt + 2]; }
+
+            // ---- layer 0 (FP32): a0 = sin(W0' x + b0'), da0_i = cos(.) * W0'[:, i]  -> region P ----------------
+#pragma unroll 1
+            for (int mi = 0; mi < 4; ++mi) {
+                const int m = grp + 2 * mi;
+                uint32_t o[32];
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    float r2[2];
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const int f = 32 * m + i + u;
+                        const float4 w = s_w0[f];
+                        float z = fmaf(w.x, px, s_b0[f]);
+                        z = fmaf(w.y, py, z);
+                        z = fmaf(w.z, pz, z);
+                        const float s = sin_reduced(z + phase0);
+                        const float mult = c == 0 ? 1.f : (c == 1 ? w.x : (c == 2 ? w.y : w.z));
+                        r2[u] = s * mult;
+                    }
+                    split_pack<PRECISE>(r2[0], r2[1], o[i >> 1], o[16 + (i >> 1)]);
+                }
+                const uint32_t addr = regionP + lane_off + 32u * (uint32_t)m;
+                if (PRECISE) { TC_ST32(addr, o); } else { TC_ST16(addr, o); }
+                tc_wait_st();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar(kBarAReady + m));
+            }
+
+            // ---- hidden layers 1..3: D (FP32, region regD) -> activations in place --------------------------------
+#pragma unroll 1
+            for (int l = 0; l < 3; ++l) {
+                const uint32_t regD = (l & 1) ? regionP : regionQ;
+                const float inv_scale = s_misc[l];
+                const float* bl = s_bias + l * 512;
+                mbar_wait(bar(kBarDFull), dphase);
+                dphase ^= 1u;
+                tc_fence_after();
+#pragma unroll 1
+                for (int mi = 0; mi < 4; ++mi) {
+                    const int m = grp + 2 * mi;
+                    const uint32_t addr = regD + lane_off + 32u * (uint32_t)m;
+                    uint32_t v[32];
+                    TC_LD32(addr, v);
+                    tc_wait_ld();
+                    uint32_t o[32];
+#pragma unroll
+                    for (int i = 0; i < 32; i += 2) {
+                        float r2[2];
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            const int f = 32 * m + i + u;
+                            const float own = __uint_as_float(v[i + u]);
+                            float zv = own;
+                            if (ORDER == 1) zv = __shfl_sync(0xffffffffu, own, qbase);
+                            const float arg = fmaf(zv, inv_scale, bl[2 * f]);  // + b' (+ pi/2 on tangent rows)
+                            const float s = sin_mufu(arg);
+                            const float mult = (ORDER == 1 && c != 0) ? own * inv_scale : 1.f;
+                            r2[u] = s * mult;
+                        }
+                        split_pack<PRECISE>(r2[0], r2[1], o[i >> 1], o[16 + (i >> 1)]);
+                    }
+                    if (PRECISE) { TC_ST32(addr, o); } else { TC_ST16(addr, o); }
+                    tc_wait_st();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar(kBarAReady + m));
+                }
+            }
+
+            // ---- output layer: D_out in region P columns [0,16) ---------------------------------------------------
+            mbar_wait(bar(kBarDFull), dphase);
+            dphase ^= 1u;
+            tc_fence_after();
+            if (grp == 0) {
+                uint32_t v[16];
+                TC_LD16(regionP + lane_off, v);
+                tc_wait_ld();
+                if (pvalid) {
+                    const float inv_out = s_misc[3];
+#pragma unroll
+                    for (int o = 0; o < 8; ++o) {
+                        if (o < out_f) {
+                            const float val = __uint_as_float(v[o]) * inv_out;
+                            if (c == 0) y[pt * out_f + o] = val + s_misc[4 + o];
+                            else J[(pt * out_f + o) * 3 + (c - 1)] = val;
+                        }
+                    }
+                }
+            }
+            // all epilogue warps passed d_full(out): the MMA warp has consumed every a_ready phase of this tile,
+            // so the next tile's layer 0 may overwrite region P
+        }
+    }
+
+    // ---- teardown ------------------------------------------------------------------------------------------------
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+    }
+}
+
+// ---- pack-time kernels ---------------------------------------------------------------------------------------------
+__global__ void tc_maxabs_kernel(const float* __restrict__ W, int count, uint32_t* __restrict__ slot) {
+    float m = 0.f;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) m = fmaxf(m, fabsf(W[i]));
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(slot, __float_as_uint(m));
+}
+
+// power-of-two scale that puts max |w * mul| into [8, 16): FP16 hi AND lo parts stay normal numbers
+__device__ __forceinline__ float pow2_scale(float maxabs) {
+    if (!(maxabs > 0.f) || !isfinite(maxabs)) return 1.f;
+    int e;
+    frexpf(maxabs, &e);            // maxabs = m * 2^e, m in [0.5, 1)
+    return ldexpf(1.f, 4 - e);     // maxabs * scale in [8, 16)
+}
+
+__global__ void tc_pack_hidden_kernel(const float* __restrict__ W, const float* __restrict__ b, float omega0, int layer,
+                                      char* __restrict__ tc) {
+    const uint32_t* mx = reinterpret_cast<const uint32_t*>(tc + kTcOffMaxAbs);
+    const float scale = pow2_scale(omega0 * __uint_as_float(mx[layer]));
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx == 0) reinterpret_cast<float*>(tc + kTcOffScales)[layer] = 1.f / scale;
+    if (idx < 256) {
+        float* bp = reinterpret_cast<float*>(tc + kTcOffBias) + (size_t)layer * 512 + 2 * idx;
+        const float bb = omega0 * b[idx];
+        bp[0] = bb;
+        bp[1] = bb + kHalfPi;
+    }
+    if (idx >= 256 * 256) return;
+    const int nrow = idx >> 8, k = idx & 255;
+    const float v = omega0 * W[idx] * scale;
+    const __half hi = __float2half_rn(v);
+    const __half lo = __float2half_rn(v - __half2float(hi));
+    const int stage = k >> 5, j = (k >> 4) & 1, kc = (k >> 3) & 1, ng = nrow >> 3;
+    const size_t off = (size_t)layer * kLayerImgBytes + (size_t)stage * kStageBytes + (size_t)j * 8192 + (size_t)kc * 4096 +
+                       (size_t)ng * 128 + (size_t)(nrow & 7) * 16 + (size_t)(k & 7) * 2;
+    char* img = tc + kTcOffHidImg;
+    *reinterpret_cast<__half*>(img + off) = hi;
+    *reinterpret_cast<__half*>(img + off + 16384) = lo;
+}
+
+__global__ void tc_pack_out_kernel(const float* __restrict__ W, const float* __restrict__ b, int out_f,
+                                   char* __restrict__ tc) {
+    const uint32_t* mx = reinterpret_cast<const uint32_t*>(tc + kTcOffMaxAbs);
+    const float scale = pow2_scale(__uint_as_float(mx[3]));
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx == 0) reinterpret_cast<float*>(tc + kTcOffScales)[3] = 1.f / scale;
+    if (idx < 8) reinterpret_cast<float*>(tc + kTcOffB4)[idx] = idx < out_f ? b[idx] : 0.f;
+    if (idx >= 16 * 256) return;
+    const int nrow = idx >> 8, k = idx & 255;
+    const float v = nrow < out_f ? W[nrow * 256 + k] * scale : 0.f;
+    const __half hi = __float2half_rn(v);
+    const __half lo = __float2half_rn(v - __half2float(hi));
+    const int t = k >> 4, kc = (k >> 3) & 1, ng = nrow >> 3;
+    const size_t off = (size_t)t * 512 + (size_t)kc * 256 + (size_t)ng * 128 + (size_t)(nrow & 7) * 16 + (size_t)(k & 7) * 2;
+    char* img = tc + kTcOffOutImg;
+    *reinterpret_cast<__half*>(img + off) = hi;
+    *reinterpret_cast<__half*>(img + off + 8192) = lo;
+}
+
+template <int ORDER, bool PRECISE>
+int launch_tc(const void* packed, const SirenHeader& h, const float* x, int64_t n, float* y, float* J,
+              cudaStream_t stream) {
+    auto kern = siren_tc_kernel<ORDER, PRECISE>;
+    const int smem = (int)kSmemTotal + 1024;
+    INF3DP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    constexpr int kPts = ORDER == 1 ? 32 : 128;
+    const int64_t tiles = (n + kPts - 1) / kPts;
+    const int grid = (int)(tiles < (int64_t)num_sms() ? tiles : (int64_t)num_sms());
+    kern<<<grid, kThreadsTc, smem, stream>>>((const char*)packed, h, x, n, y, J);
+    INF3DP_LAUNCH_CHECK("siren_tc_kernel");
     return INF3DP_OK;
 }
 
-int siren_tc_launch(const void*, const SirenHeader&, const float*, int64_t, int, float*, float*, bool, cudaStream_t) {
-    set_error("tensor-core engine not built");
-    return INF3DP_EINVAL;
+}  // namespace
+
+size_t siren_tc_section_bytes() { return kTcSectionBytes; }
+
+int siren_tc_pack(const float* const* W, const float* const* b, float omega0, int out_features, void* packed,
+                  const SirenLayout& lay, SirenHeader& hdr, cudaStream_t stream) {
+    char* tc = (char*)packed + lay.off_tc;
+    INF3DP_CUDA(cudaMemsetAsync(tc, 0, kTcOffHidImg, stream));  // scales, max-abs scratch, out image padding rows
+    uint32_t* mx = reinterpret_cast<uint32_t*>(tc + kTcOffMaxAbs);
+    for (int l = 0; l < 3; ++l) {
+        tc_maxabs_kernel<<<64, 256, 0, stream>>>(W[1 + l], 256 * 256, mx + l);
+        INF3DP_LAUNCH_CHECK("tc_maxabs_kernel");
+    }
+    tc_maxabs_kernel<<<4, 256, 0, stream>>>(W[4], out_features * 256, mx + 3);
+    INF3DP_LAUNCH_CHECK("tc_maxabs_kernel");
+    for (int l = 0; l < 3; ++l) {
+        tc_pack_hidden_kernel<<<256, 256, 0, stream>>>(W[1 + l], b[1 + l], omega0, l, tc);
+        INF3DP_LAUNCH_CHECK("tc_pack_hidden_kernel");
+    }
+    tc_pack_out_kernel<<<16, 256, 0, stream>>>(W[4], b[4], out_features, tc);
+    INF3DP_LAUNCH_CHECK("tc_pack_out_kernel");
+    hdr.tc_ok = 1;
+    return INF3DP_OK;
+}
+
+int siren_tc_launch(const void* packed, const SirenHeader& h, const float* x, int64_t n, int order, float* y,
+                    float* J, bool precise, cudaStream_t stream) {
+    INF3DP_CHECK_ARG(h.tc_ok && h.off_tc != 0, "siren_tc: packed weights carry no tensor-core section");
+    if (order == 0) return precise ? launch_tc<0, true>(packed, h, x, n, y, J, stream)
+                                   : launch_tc<0, false>(packed, h, x, n, y, J, stream);
+    return precise ? launch_tc<1, true>(packed, h, x, n, y, J, stream)
+                   : launch_tc<1, false>(packed, h, x, n, y, J, stream);
 }
 
 }  // namespace inf3dp
