@@ -19,13 +19,17 @@
 //     lanes run one MUFU.SIN per feature), split to FP16 hi/lo and write the next layer's A operand with tcgen05.st
 //     IN PLACE over the accumulator columns they just consumed.  The two halves of tensor memory swap roles every
 //     layer; the loop over K is the outer MMA loop (N = 256 per instruction), so the MMAs of layer l+1 start as
-//     soon as the first 32-feature slice of layer l's activations is written and overlap the rest of the epilogue.
+//     soon as the first 16-feature slice of layer l's activations is written and overlap the rest of the epilogue.
 //   * Layer 0 (3 -> 256) and the omega0 folding are FP32 CUDA-core work (north_star), the output layer is a
 //     128 x 16 x 256 MMA.
-// Warp roles (320 threads): warps 0-7 epilogue (two warps per TMEM lane quadrant, interleaved 32-column slices),
-// warp 8 weight producer (one elected lane), warp 9 TMEM allocator + MMA issuer (one elected lane).
+// Warp roles (576 threads): warps 0-15 epilogue (four warps per TMEM lane quadrant, interleaved 16-feature
+// slices = one MMA K-step each), warp 16 weight producer (one elected lane), warp 17 TMEM allocator + MMA issuer
+// (one elected lane).  Within a 256-column half of tensor memory, K-step t of the A operand lives in columns
+// [16t, 16t+8) (FP16 hi, two features per column) and [16t+8, 16t+16) (FP16 lo): exactly the 16 FP32 accumulator
+// columns the slice was computed from, which is what makes the in-place conversion hazard-free.
 // Every mbarrier wait carries a watchdog that traps instead of hanging the GPU.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -45,21 +49,24 @@ constexpr size_t kLayerImgBytes = 8 * kStageBytes;
 constexpr size_t kTcSectionBytes = kTcOffHidImg + 3 * kLayerImgBytes;
 
 // ---- shared memory layout -----------------------------------------------------------------------------------
-constexpr int kStages = 6;
+constexpr int kStages = 3;                 // ring stages of 4 K-steps (2 consecutive 32 KB image stages)
+constexpr uint32_t kRingStageBytes = 2 * kStageBytes;
 constexpr uint32_t kSmemRing = 0;
-constexpr uint32_t kSmemOutImg = kStages * kStageBytes;              // 196608
+constexpr uint32_t kSmemOutImg = kStages * kRingStageBytes;          // 196608
 constexpr uint32_t kSmemBias = kSmemOutImg + 16384;                  // 212992
 constexpr uint32_t kSmemW0 = kSmemBias + 6144;                       // 219136
 constexpr uint32_t kSmemB0 = kSmemW0 + 4096;                         // 223232
 constexpr uint32_t kSmemMisc = kSmemB0 + 1024;                       // 224256: inv_scale[4], b4[8]
 constexpr uint32_t kSmemBars = kSmemMisc + 64;                       // 224320
-constexpr int kBarWFull = 0, kBarWEmpty = kStages, kBarAReady = 2 * kStages, kBarDFull = 2 * kStages + 8,
-              kBarOutImg = 2 * kStages + 9, kNumBars = 2 * kStages + 10;
+constexpr int kBarWFull = 0, kBarWEmpty = kStages, kBarAReady = 2 * kStages, kBarDFull = 2 * kStages + 4,
+              kBarOutImg = 2 * kStages + 5, kNumBars = 2 * kStages + 6;
 constexpr uint32_t kSmemTmemPtr = kSmemBars + kNumBars * 8;
 constexpr uint32_t kSmemTotal = kSmemTmemPtr + 16;
 static_assert(kSmemTotal <= 232448 - 1024, "shared memory budget (1 KB reserved for base alignment)");
 
-constexpr int kThreadsTc = 320;
+constexpr int kEpiWarps = 16;
+constexpr int kProducerWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;
+constexpr int kThreadsTc = (kEpiWarps + 2) * 32;  // 576
 constexpr float kHalfPi = 1.57079632679489662f;
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------------------
@@ -84,14 +91,28 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 // Wait with a watchdog: a protocol bug traps (launch failure) instead of hanging the device.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
+    uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000ll) {
+        if (++spins > 16u) __nanosleep(40);
+        if (spins > (1u << 24)) {  // >~ 1 s: a protocol bug, not a slow kernel
             printf("inf3dp siren_tc: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x,
                    threadIdx.x, bar, parity);
             __trap();
         }
     }
+}
+// One lane polls, the warp follows (keeps 31 lanes' worth of spin instructions out of the issue slots).
+__device__ __forceinline__ void mbar_wait_timed(uint32_t bar, uint32_t parity, unsigned long long* acc);
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity, int lane, unsigned long long* acc = nullptr) {
+    if (lane == 0) mbar_wait_timed(bar, parity, acc);
+    __syncwarp();
+}
+// Developer instrumentation (INF3DP_TC_DEBUG=1): cycles spent blocked in a wait, accumulated per role.
+__device__ __forceinline__ void mbar_wait_timed(uint32_t bar, uint32_t parity, unsigned long long* acc) {
+    if (acc == nullptr) { mbar_wait(bar, parity); return; }
+    const long long t0 = clock64();
+    mbar_wait(bar, parity);
+    *acc += (unsigned long long)(clock64() - t0);
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -151,6 +172,11 @@ __host__ __device__ constexpr uint32_t make_idesc(int n) {
                    "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]),   \
                    "r"(v[15]) : "memory")
 
+#define TC_ST8(addr, v)                                                                                          \
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"                         \
+                 ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]),        \
+                   "r"(v[7]) : "memory")
+
 #define TC_LD16(addr, v)                                                                                         \
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "                                                       \
                  "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"                                \
@@ -167,12 +193,19 @@ __device__ __forceinline__ float sin_mufu(float x) {
     asm("sin.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
-// FP32 argument reduction to [-pi, pi] (two-constant Cody-Waite), then MUFU: used for layer 0 where |z| reaches ~50.
-__device__ __forceinline__ float sin_reduced(float x) {
-    const float k = rintf(x * 0.15915494309189535f);
-    float r = fmaf(-k, 6.28318548202514648f, x);        // 2*pi rounded to FP32
-    r = fmaf(-k, -1.74845553146951715e-7f, r);           // 2*pi - fl(2*pi)
-    return sin_mufu(r);
+// Layer 0 arguments reach |z| ~ 50 rad (30 * (|W0 x| + |b0|)).  MUFU.SIN reduces modulo one revolution itself
+// after the x * 1/(2 pi) scaling that sin.approx performs in FP32, so the absolute phase error grows like
+// |z| * 2^-24 * 2 pi ~ 2e-5 rad at |z| = 50; two-constant Cody-Waite reduction first keeps it at the 1e-6 level
+// for ~4 more FP32 instructions per feature.  PRECISE keeps the reduction, FAST drops it.
+template <bool PRECISE>
+__device__ __forceinline__ float sin_layer0(float x) {
+    if (PRECISE) {
+        const float k = rintf(x * 0.15915494309189535f);
+        float r = fmaf(-k, 6.28318548202514648f, x);        // 2*pi rounded to FP32
+        r = fmaf(-k, -1.74845553146951715e-7f, r);           // 2*pi - fl(2*pi)
+        return sin_mufu(r);
+    }
+    return sin_mufu(x);
 }
 
 // Split two FP32 values into packed FP16 hi and lo words (value 0 in the low half = lower feature index).
@@ -193,7 +226,7 @@ __device__ __forceinline__ void split_pack(float o0, float o1, uint32_t& hi, uin
 template <int ORDER, bool PRECISE>
 __global__ void __launch_bounds__(kThreadsTc, 1)
 siren_tc_kernel(const char* __restrict__ packed, SirenHeader h, const float* __restrict__ x, int64_t n,
-                float* __restrict__ y, float* __restrict__ J) {
+                float* __restrict__ y, float* __restrict__ J, unsigned long long* __restrict__ dbg) {
     extern __shared__ unsigned char smem_dyn[];
     // 1 KB alignment for the bulk-copy destinations / UMMA operands
     const uint32_t sbase = (smem_u32(smem_dyn) + 1023u) & ~1023u;
@@ -214,7 +247,7 @@ siren_tc_kernel(const char* __restrict__ packed, SirenHeader h, const float* __r
     // ---- one-time setup --------------------------------------------------------------------------------------
     if (tid == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(bar(kBarWFull + s), 1); mbar_init(bar(kBarWEmpty + s), 1); }
-        for (int m = 0; m < 8; ++m) mbar_init(bar(kBarAReady + m), 4);
+        for (int r = 0; r < 4; ++r) mbar_init(bar(kBarAReady + r), kEpiWarps);  // round r: every warp's r-th slice
         mbar_init(bar(kBarDFull), 1);
         mbar_init(bar(kBarOutImg), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -233,7 +266,7 @@ siren_tc_kernel(const char* __restrict__ packed, SirenHeader h, const float* __r
         if (tid < 4) s_misc[tid] = reinterpret_cast<const float*>(tc + kTcOffScales)[tid];
         if (tid >= 4 && tid < 12) s_misc[tid] = reinterpret_cast<const float*>(tc + kTcOffB4)[tid - 4];
     }
-    if (warp == 9) {  // TMEM: all 512 columns (one CTA per SM by construction: ~219 KB of shared memory)
+    if (warp == kMmaWarp) {  // TMEM: all 512 columns (one CTA per SM by construction: ~219 KB of shared memory)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                      ::"r"(sbase + kSmemTmemPtr), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -244,86 +277,116 @@ siren_tc_kernel(const char* __restrict__ packed, SirenHeader h, const float* __r
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sptr + kSmemTmemPtr);
     const uint32_t regionP = tmem, regionQ = tmem + 256;
 
-    if (warp == 8) {
+    if (warp == kProducerWarp) {
         // ================= weight producer =====================================================================
         if (lane == 0) {
             mbar_expect_tx(bar(kBarOutImg), 16384);
             bulk_g2s(sbase + kSmemOutImg, tc + kTcOffOutImg, 16384, bar(kBarOutImg));
-            const uint32_t copy_bytes = PRECISE ? (uint32_t)kStageBytes : (uint32_t)(kStageBytes / 2);
             uint32_t stage = 0, phase = 0;
             for (int it = 0; it < my_tiles; ++it) {
                 for (int l = 0; l < 3; ++l) {
                     const char* img = tc + kTcOffHidImg + (size_t)l * kLayerImgBytes;
-                    for (int s = 0; s < 8; ++s) {
+                    for (int s = 0; s < 4; ++s) {  // 4 K-steps per ring stage
                         mbar_wait(bar(kBarWEmpty + stage), phase ^ 1u);
-                        mbar_expect_tx(bar(kBarWFull + stage), copy_bytes);
-                        bulk_g2s(sbase + kSmemRing + stage * (uint32_t)kStageBytes, img + (size_t)s * kStageBytes,
-                                 copy_bytes, bar(kBarWFull + stage));
+                        const uint32_t dst = sbase + kSmemRing + stage * kRingStageBytes;
+                        const char* src = img + (size_t)s * kRingStageBytes;
+                        if (PRECISE) {
+                            mbar_expect_tx(bar(kBarWFull + stage), kRingStageBytes);
+                            bulk_g2s(dst, src, kRingStageBytes, bar(kBarWFull + stage));
+                        } else {  // FP16 hi halves only (first 16 KB of each 32 KB image stage)
+                            mbar_expect_tx(bar(kBarWFull + stage), 32768u);
+                            bulk_g2s(dst, src, 16384u, bar(kBarWFull + stage));
+                            bulk_g2s(dst + 32768u, src + 32768, 16384u, bar(kBarWFull + stage));
+                        }
                         if (++stage == kStages) { stage = 0; phase ^= 1u; }
                     }
                 }
             }
         }
-    } else if (warp == 9) {
+    } else if (warp == kMmaWarp) {
         // ================= MMA issuer ===========================================================================
         if (lane == 0) {
             constexpr uint32_t idesc256 = make_idesc(256);
             constexpr uint32_t idesc16 = make_idesc(16);
             uint32_t stage = 0, wphase = 0;
             uint32_t aphase = 0;  // parity of the a_ready barriers (one completion per activation version)
+            unsigned long long wait_a = 0, wait_w = 0, dbg_lag = 0;
+            uint32_t dbg_dphase = 0;
+            unsigned long long* pa = dbg ? &wait_a : nullptr;
+            unsigned long long* pw = dbg ? &wait_w : nullptr;
+            const long long t_begin = clock64();
             mbar_wait(bar(kBarOutImg), 0);
             for (int it = 0; it < my_tiles; ++it) {
                 // hidden layers 1..3: A alternates P,Q,P ; D alternates Q,P,Q
                 for (int l = 0; l < 3; ++l) {
                     const uint32_t regA = (l & 1) ? regionQ : regionP;
                     const uint32_t regD = (l & 1) ? regionP : regionQ;
-                    for (int t = 0; t < 16; ++t) {
-                        if ((t & 1) == 0) {
-                            mbar_wait(bar(kBarAReady + (t >> 1)), aphase);
-                            mbar_wait(bar(kBarWFull + stage), wphase);
-                            tc_fence_after();
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        mbar_wait_timed(bar(kBarAReady + r), aphase, pa);   // K-steps 4r..4r+3 of the activations
+                        mbar_wait_timed(bar(kBarWFull + stage), wphase, pw);
+                        tc_fence_after();
+                        const uint32_t ring = sbase + kSmemRing + stage * kRingStageBytes;
+#pragma unroll
+                        for (int tt = 0; tt < 4; ++tt) {
+                            const int t = 4 * r + tt;
+                            const uint32_t sb = ring + (uint32_t)(tt >> 1) * 32768u + (uint32_t)(tt & 1) * 8192u;
+                            const uint64_t bh = make_desc(sb, 4096, 128);
+                            const uint32_t a_hi = regA + 16u * (uint32_t)t;
+                            mma_ts(regD, a_hi, bh, idesc256, t > 0 ? 1u : 0u);
+                            if (PRECISE) {
+                                const uint64_t bl = make_desc(sb + 16384u, 4096, 128);
+                                mma_ts(regD, a_hi + 8u, bh, idesc256, 1u);
+                                mma_ts(regD, a_hi, bl, idesc256, 1u);
+                            }
                         }
-                        const uint32_t sb = sbase + kSmemRing + stage * (uint32_t)kStageBytes + (uint32_t)(t & 1) * 8192u;
-                        const uint64_t bh = make_desc(sb, 4096, 128);
-                        const uint32_t a_hi = regA + 32u * (uint32_t)(t >> 1) + 8u * (uint32_t)(t & 1);
-                        mma_ts(regD, a_hi, bh, idesc256, t > 0 ? 1u : 0u);
-                        if (PRECISE) {
-                            const uint64_t bl = make_desc(sb + 16384u, 4096, 128);
-                            mma_ts(regD, a_hi + 16u, bh, idesc256, 1u);
-                            mma_ts(regD, a_hi, bl, idesc256, 1u);
-                        }
-                        if (t & 1) {
-                            tc_commit(bar(kBarWEmpty + stage));  // stage free once these MMAs have read it
-                            if (++stage == kStages) { stage = 0; wphase ^= 1u; }
-                        }
+                        tc_commit(bar(kBarWEmpty + stage));  // stage free once these MMAs have read it
+                        if (++stage == kStages) { stage = 0; wphase ^= 1u; }
                     }
                     tc_commit(bar(kBarDFull));
+                    if (dbg) {  // instrumentation only: how long after the last issue does D become visible?
+                        const long long t0 = clock64();
+                        mbar_wait(bar(kBarDFull), dbg_dphase);
+                        dbg_lag += (unsigned long long)(clock64() - t0);
+                    }
+                    dbg_dphase ^= 1u;
                     aphase ^= 1u;
                 }
                 // output layer: A = activations of layer 3 (region Q), D = region P columns [0,16)
-                for (int t = 0; t < 16; ++t) {
-                    if ((t & 1) == 0) {
-                        mbar_wait(bar(kBarAReady + (t >> 1)), aphase);
-                        tc_fence_after();
-                    }
-                    const uint32_t sb = sbase + kSmemOutImg + (uint32_t)t * 512u;
-                    const uint64_t bh = make_desc(sb, 256, 128);
-                    const uint32_t a_hi = regionQ + 32u * (uint32_t)(t >> 1) + 8u * (uint32_t)(t & 1);
-                    mma_ts(regionP, a_hi, bh, idesc16, t > 0 ? 1u : 0u);
-                    if (PRECISE) {
-                        const uint64_t bl = make_desc(sb + 8192u, 256, 128);
-                        mma_ts(regionP, a_hi + 16u, bh, idesc16, 1u);
-                        mma_ts(regionP, a_hi, bl, idesc16, 1u);
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    mbar_wait_timed(bar(kBarAReady + r), aphase, pa);
+                    tc_fence_after();
+#pragma unroll
+                    for (int tt = 0; tt < 4; ++tt) {
+                        const int t = 4 * r + tt;
+                        const uint32_t sb = sbase + kSmemOutImg + (uint32_t)t * 512u;
+                        const uint64_t bh = make_desc(sb, 256, 128);
+                        const uint32_t a_hi = regionQ + 16u * (uint32_t)t;
+                        mma_ts(regionP, a_hi, bh, idesc16, t > 0 ? 1u : 0u);
+                        if (PRECISE) {
+                            const uint64_t bl = make_desc(sb + 8192u, 256, 128);
+                            mma_ts(regionP, a_hi + 8u, bh, idesc16, 1u);
+                            mma_ts(regionP, a_hi, bl, idesc16, 1u);
+                        }
                     }
                 }
                 tc_commit(bar(kBarDFull));
+                dbg_dphase ^= 1u;
                 aphase ^= 1u;
+            }
+            if (dbg && blockIdx.x == 0) {
+                dbg[4] = dbg_lag;
+                dbg[0] = (unsigned long long)(clock64() - t_begin);
+                dbg[1] = wait_a;
+                dbg[2] = wait_w;
+                dbg[3] = (unsigned long long)my_tiles;
             }
         }
     } else {
-        // ================= epilogue warps 0..7 ===================================================================
+        // ================= epilogue warps 0..15 ==================================================================
         const int quad = warp & 3;           // TMEM lane quadrant this warp may access
-        const int grp = warp >> 2;           // 0: slices 0,2,4,6   1: slices 1,3,5,7
+        const int grp = warp >> 2;           // slices grp, grp+4, grp+8, grp+12 (one MMA K-step each)
         const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
         const int row = quad * 32 + lane;    // TMEM lane = tile row
         const int c = ORDER == 1 ? (lane & 3) : 0;          // jet column of this row
@@ -335,6 +398,8 @@ siren_tc_kernel(const char* __restrict__ packed, SirenHeader h, const float* __r
         const float* s_misc = reinterpret_cast<const float*>(sptr + kSmemMisc);
         const float phase0 = c != 0 ? kHalfPi : 0.f;
         uint32_t dphase = 0;
+        unsigned long long wait_d = 0;
+        unsigned long long* pd = (dbg && lane == 0) ? &wait_d : nullptr;
 
         for (int it = 0; it < my_tiles; ++it) {
             const int64_t tile = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
@@ -346,75 +411,82 @@ siren_tc_kernel(const char* __restrict__ packed, SirenHeader h, const float* __r
             // ---- layer 0 (FP32): a0 = sin(W0' x + b0'), da0_i = cos(.) * W0'[:, i]  -> region P ----------------
 #pragma unroll 1
             for (int mi = 0; mi < 4; ++mi) {
-                const int m = grp + 2 * mi;
-                uint32_t o[32];
+                const int m = grp + 4 * mi;
+                uint32_t o[16];
 #pragma unroll
-                for (int i = 0; i < 32; i += 2) {
+                for (int i = 0; i < 16; i += 2) {
                     float r2[2];
 #pragma unroll
                     for (int u = 0; u < 2; ++u) {
-                        const int f = 32 * m + i + u;
+                        const int f = 16 * m + i + u;
                         const float4 w = s_w0[f];
                         float z = fmaf(w.x, px, s_b0[f]);
                         z = fmaf(w.y, py, z);
                         z = fmaf(w.z, pz, z);
-                        const float s = sin_reduced(z + phase0);
+                        const float s = sin_layer0<PRECISE>(z + phase0);
                         const float mult = c == 0 ? 1.f : (c == 1 ? w.x : (c == 2 ? w.y : w.z));
                         r2[u] = s * mult;
                     }
-                    split_pack<PRECISE>(r2[0], r2[1], o[i >> 1], o[16 + (i >> 1)]);
+                    split_pack<PRECISE>(r2[0], r2[1], o[i >> 1], o[8 + (i >> 1)]);
                 }
-                const uint32_t addr = regionP + lane_off + 32u * (uint32_t)m;
-                if (PRECISE) { TC_ST32(addr, o); } else { TC_ST16(addr, o); }
+                const uint32_t addr = regionP + lane_off + 16u * (uint32_t)m;
+                if (PRECISE) { TC_ST16(addr, o); } else { TC_ST8(addr, o); }
                 tc_wait_st();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar(kBarAReady + m));
+                if (lane == 0) mbar_arrive(bar(kBarAReady + mi));
             }
 
             // ---- hidden layers 1..3: D (FP32, region regD) -> activations in place --------------------------------
+            // per-lane constants so that value and tangent rows run the same instruction stream:
+            //   out = sin(z_value * inv + b (+ pi/2)) * (own * k1 + k0),  (k1,k0) = (0,1) value row, (inv,0) tangent row
 #pragma unroll 1
             for (int l = 0; l < 3; ++l) {
                 const uint32_t regD = (l & 1) ? regionP : regionQ;
                 const float inv_scale = s_misc[l];
+                const float k1 = (ORDER == 1 && c != 0) ? inv_scale : 0.f;
+                const float k0 = (ORDER == 1 && c != 0) ? 0.f : 1.f;
                 const float* bl = s_bias + l * 512;
-                mbar_wait(bar(kBarDFull), dphase);
+                mbar_wait_warp(bar(kBarDFull), dphase, lane, pd);
                 dphase ^= 1u;
                 tc_fence_after();
+                uint32_t v[16];
+                TC_LD16(regD + lane_off + 16u * (uint32_t)grp, v);
 #pragma unroll 1
                 for (int mi = 0; mi < 4; ++mi) {
-                    const int m = grp + 2 * mi;
-                    const uint32_t addr = regD + lane_off + 32u * (uint32_t)m;
-                    uint32_t v[32];
-                    TC_LD32(addr, v);
+                    const int m = grp + 4 * mi;
+                    const uint32_t addr = regD + lane_off + 16u * (uint32_t)m;
                     tc_wait_ld();
-                    uint32_t o[32];
+                    float cur[16];
 #pragma unroll
-                    for (int i = 0; i < 32; i += 2) {
+                    for (int i = 0; i < 16; ++i) cur[i] = __uint_as_float(v[i]);
+                    if (mi < 3) TC_LD16(addr + 64u, v);  // prefetch the next slice (columns 16*(m+4)) under the math
+                    uint32_t o[16];
+#pragma unroll
+                    for (int i = 0; i < 16; i += 2) {
                         float r2[2];
 #pragma unroll
                         for (int u = 0; u < 2; ++u) {
-                            const int f = 32 * m + i + u;
-                            const float own = __uint_as_float(v[i + u]);
+                            const int f = 16 * m + i + u;
+                            const float own = cur[i + u];
                             float zv = own;
                             if (ORDER == 1) zv = __shfl_sync(0xffffffffu, own, qbase);
                             const float arg = fmaf(zv, inv_scale, bl[2 * f]);  // + b' (+ pi/2 on tangent rows)
                             const float s = sin_mufu(arg);
-                            const float mult = (ORDER == 1 && c != 0) ? own * inv_scale : 1.f;
-                            r2[u] = s * mult;
+                            r2[u] = ORDER == 1 ? s * fmaf(own, k1, k0) : s;
                         }
-                        split_pack<PRECISE>(r2[0], r2[1], o[i >> 1], o[16 + (i >> 1)]);
+                        split_pack<PRECISE>(r2[0], r2[1], o[i >> 1], o[8 + (i >> 1)]);
                     }
-                    if (PRECISE) { TC_ST32(addr, o); } else { TC_ST16(addr, o); }
+                    if (PRECISE) { TC_ST16(addr, o); } else { TC_ST8(addr, o); }
                     tc_wait_st();
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(bar(kBarAReady + m));
+                    if (lane == 0) mbar_arrive(bar(kBarAReady + mi));
                 }
             }
 
             // ---- output layer: D_out in region P columns [0,16) ---------------------------------------------------
-            mbar_wait(bar(kBarDFull), dphase);
+            mbar_wait_warp(bar(kBarDFull), dphase, lane, pd);
             dphase ^= 1u;
             tc_fence_after();
             if (grp == 0) {
@@ -436,12 +508,13 @@ siren_tc_kernel(const char* __restrict__ packed, SirenHeader h, const float* __r
             // all epilogue warps passed d_full(out): the MMA warp has consumed every a_ready phase of this tile,
             // so the next tile's layer 0 may overwrite region P
         }
+        if (dbg && blockIdx.x == 0 && lane == 0) dbg[8 + warp] = wait_d;
     }
 
     // ---- teardown ------------------------------------------------------------------------------------------------
     tc_fence_before();
     __syncthreads();
-    if (warp == 9) {
+    if (warp == kMmaWarp) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
     }
 }
@@ -515,8 +588,24 @@ int launch_tc(const void* packed, const SirenHeader& h, const float* x, int64_t 
     constexpr int kPts = ORDER == 1 ? 32 : 128;
     const int64_t tiles = (n + kPts - 1) / kPts;
     const int grid = (int)(tiles < (int64_t)num_sms() ? tiles : (int64_t)num_sms());
-    kern<<<grid, kThreadsTc, smem, stream>>>((const char*)packed, h, x, n, y, J);
+    static const bool debug = getenv("INF3DP_TC_DEBUG") != nullptr;
+    unsigned long long* dbg = nullptr;
+    if (debug) {
+        INF3DP_CUDA(cudaMalloc(&dbg, 64 * sizeof(unsigned long long)));
+        INF3DP_CUDA(cudaMemsetAsync(dbg, 0, 64 * sizeof(unsigned long long), stream));
+    }
+    kern<<<grid, kThreadsTc, smem, stream>>>((const char*)packed, h, x, n, y, J, dbg);
     INF3DP_LAUNCH_CHECK("siren_tc_kernel");
+    if (debug) {
+        unsigned long long hbuf[64];
+        INF3DP_CUDA(cudaMemcpyAsync(hbuf, dbg, sizeof(hbuf), cudaMemcpyDeviceToHost, stream));
+        INF3DP_CUDA(cudaStreamSynchronize(stream));
+        INF3DP_CUDA(cudaFree(dbg));
+        const double tiles = hbuf[3] ? (double)hbuf[3] : 1.0;
+        fprintf(stderr, "[inf3dp tc debug] block0: %.0f tiles, %.0f cyc/tile; MMA warp blocked on a_ready %.0f, on w_full %.0f cyc/tile; "
+                        "epilogue warp0 blocked on d_full %.0f, warp5 %.0f, warp15 %.0f cyc/tile; issue->D visible lag %.0f cyc/tile (3 hidden layers)\n",
+                tiles, hbuf[0] / tiles, hbuf[1] / tiles, hbuf[2] / tiles, hbuf[8] / tiles, hbuf[13] / tiles, hbuf[23] / tiles, hbuf[4] / tiles);
+    }
     return INF3DP_OK;
 }
 
