@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native INF-3DP hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    (N > 1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...)
+
+Metric (BASELINE.json): SIREN value+grad points/s.  Workload at every N: BASELINE.json configs[1], the dense
+512^3 grid evaluation with normals of the SDF network (sdf_meshing path): coordinates = the reference's
+gen_voxle_queries(512) (134 217 728 points, shear quirk included), network = sdf_config arch
+(3->256->256->256->256->1, sine, random init seed 2048), outputs = field value, gradient and unit normal per point.
+A step is one pass over the whole grid.  With N ranks every rank evaluates its own 512^3 grid shard of an
+N*512^3-point job (weak scaling) and the step ends with one NCCL all-gather of the (value, gradient) rows.
+
+`value`  : whole-job points/s with coordinates resident in HBM (CUDA events, max over ranks).
+`e2e`    : the same metric through the public host-buffer API (inf3dp.HostPipeline): pinned host coordinates
+           -> H2D -> fused kernel -> D2H of (value, gradient) into pinned host memory, copies inside the timed region.
+`roofline`: dominant kernel (siren_tc_kernel): algorithmic FLOPs (1 576 448 per point) / launch
+           duration against the measured dense tensor peak in MEASURED_PEAKS.json.
+`cpu_baseline`: the torch-CPU port of the reference's own path (oracle/siren_torch_port.py) on the host cores.
+`--impl reference`: that CPU path alone, same metric, bounded sample per step.
+Second metric (isocontour layers/s) is carried in the `isocontour` object of the same line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "inf-3dp_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+FLOP_PER_POINT = 1_576_448          # forward-mode value+gradient, SURVEY.md section 8d
+GRID_N = 512
+WORKLOAD = "bunny SDF dense 512^3 grid evaluation (sdf_meshing path) with normals"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {"hbm": float(d["hbm_gbs"]), "tf_burst": float(d["bf16_tflops"]),
+                "tf_sustained": float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "source": "measured"}
+    return {"hbm": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "source": "fallback"}
+
+
+def golden_layers():
+    import numpy as np
+    g = np.load(os.path.join(ROOT, "tests", "golden", "siren_golden.npz"))
+    return [(g[f"sdf/net.net.{i}.0.weight"], g[f"sdf/net.net.{i}.0.bias"]) for i in range(5)]
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+            except (ValueError, IndexError):
+                continue
+            for nme, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        sm.sort()
+        med = sm[len(sm) // 2] if sm else None
+        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_port_points_per_s(sample_points, repeats, threads):
+    """The reference's torch-CPU path (oracle port): field_query_with_grads on `sample_points` grid points."""
+    import numpy as np
+    import torch
+    from oracle import siren_torch_port as port
+    from oracle import siren_oracle as so
+    torch.set_num_threads(threads)
+    model = port.PortSiren([(W.astype(np.float32), b.astype(np.float32)) for W, b in golden_layers()])
+    model.eval()
+    # a contiguous slab of the 512^3 grid (same generator as the GPU arm), bounded so the run stays short
+    side = 64
+    grid = so.gen_voxel_queries(side)
+    coords = torch.from_numpy(grid[:sample_points].copy())
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        port.field_query_with_grads(model, coords, max_batch=32 ** 3)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return sample_points / best, best
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sample = 262144
+    times = []
+    import torch
+    for i in range(args.warmup + args.steps):
+        pps, dt = cpu_port_points_per_s(sample, 1, cores)
+        if i >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    value = sample / (ms / 1e3)
+    desc = f"{sample} grid points per step (utils.field_query_with_grads, max_batch 32^3) on {cores} host threads"
+    line = {"impl": "reference", "metric": "siren_value_grad_points_per_s", "value": value, "unit": "points/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "network": "3-256-256-256-256-1 sine, seed 2048", "grid": GRID_N},
+            "cpu_baseline": {"value": value, "unit": "points/s", "cores": cores, "kind": "port", "sample": desc},
+            "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "torch": torch.__version__}
+    print(json.dumps(line), flush=True)
+
+
+def bench_isocontours(dev, peaks):
+    """BASELINE.json configs[2]: 200-isovalue isocontour extraction on a closed synthetic mesh (SURVEY.md 8d cfg 3)."""
+    import numpy as np
+    import torch
+    import inf3dp
+    from oracle import contour_oracle as co
+    V, F = co.torus_mesh(1000, 500)           # 1.0 M faces, 0.5 M vertices
+    f = (V[:, 2] + 0.25 * np.sin(3.0 * V[:, 0]) * np.cos(2.0 * V[:, 1])).astype(np.float32)
+    K = 200
+    iso = np.linspace(f.min(), f.max(), K).astype(np.float32)
+    t = [torch.from_numpy(a).to(dev) for a in (V, F, f, iso)]
+    L = inf3dp._lib.lib()
+    nV, nF = len(V), len(F)
+    merged = torch.empty((K, nF, 3), dtype=torch.float32, device=dev)
+    nums = torch.empty(K, dtype=torch.int32, device=dev)
+    wsb = L.inf3dp_extract_isocontours_workspace_bytes(nV, nF, K)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    st = inf3dp._lib.stream_ptr(dev)
+
+    def call():
+        inf3dp._lib.check(L.inf3dp_extract_isocontours(*[inf3dp._lib.ptr(a) for a in t], nV, nF, K,
+                                                       inf3dp._lib.ptr(merged), inf3dp._lib.ptr(nums),
+                                                       inf3dp._lib.ptr(ws), wsb, st))
+    for _ in range(3):
+        call()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    iters = 10
+    e0.record()
+    for _ in range(iters):
+        call()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / iters
+    seg = (inf3dp._lib.ctypes.c_int32 * K)()
+    inf3dp._lib.check(L.inf3dp_extract_isocontours_status(inf3dp._lib.ptr(ws), K, seg, st))
+    S = int(sum(seg)); C = int(nums.sum().item())
+    contract = 12 * nF + 16 * nV + 4 * K + 12 * K * nF + 4 * K
+    useful = 12 * nF + 16 * nV + 4 * K + 12 * (S + C) + 4 * K
+    return {"metric": "isocontour_layers_per_s", "value": K / (ms / 1e3), "unit": "layers/s", "ms_per_call": ms,
+            "config": {"workload": "200-isovalue isocontour extraction, closed torus mesh", "faces": nF,
+                       "vertices": nV, "isovalues": K, "segments": S, "loops": C},
+            "roofline": {"bound": "hbm", "achieved": contract / (ms / 1e3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
+                         "frac": contract / (ms / 1e3) / 1e9 / peaks["hbm"], "traffic": None,
+                         "bytes_contract": contract, "bytes_useful": useful,
+                         "useful_gbs": useful / (ms / 1e3) / 1e9, "peak_source": peaks["source"]},
+            "gpu_launches_per_call": 9}
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import inf3dp
+    from inf3dp.query import gen_voxel_queries, HostPipeline
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the inf3dp hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = load_peaks()
+    engine = os.environ.get("INF3DP_ENGINE", "tc_precise")  # the parity-passing engine is the headline
+
+    net = inf3dp.SingleBVPNet(type="sine", in_features=3)
+    net.load_state_dict({f"net.net.{i}.0.{k}": torch.from_numpy(np.asarray(v)) for i, (W, b) in enumerate(golden_layers())
+                         for k, v in (("weight", W), ("bias", b))})
+    net.to(dev)
+
+    # every rank owns one 512^3 grid of the N * 512^3 point job (weak scaling); coordinates resident in HBM
+    coords, _, _ = gen_voxel_queries(GRID_N, device=dev)
+    n = coords.shape[0]
+    normals = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    gathered = torch.empty((world * n, 4), dtype=torch.float32, device=dev) if world > 1 else None
+    launches_per_step = 2
+
+    def step():
+        y, J, _ = net.query(coords, order=1, mode=engine)       # launch 1: fused value + gradient
+        inf3dp.unit_normals(J.view(n, 3), out=normals)           # launch 2: normals
+        if world > 1:                                            # the one collective of the sharded path
+            rows = torch.cat([y, J.view(n, 3)], dim=1)
+            dist.all_gather_into_tensor(gathered, rows)
+        return y, J
+
+    # kernel-only timing of the dominant kernel (for the roofline), same stream
+    def jet_only():
+        return net.query(coords, order=1, mode=engine)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    ms_step = e0.elapsed_time(e1) / args.steps
+
+    # dominant kernel alone (CUDA events on the launching stream)
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record()
+    for _ in range(args.steps):
+        jet_only()
+    k1.record()
+    torch.cuda.synchronize(dev)
+    ms_kernel = k0.elapsed_time(k1) / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end to end through the public host-buffer API -------------------------------------------------------
+    del normals
+    coords_host = torch.empty((n, 3), dtype=torch.float32, pin_memory=True)
+    coords_host.copy_(coords)
+    out_host = torch.empty((n, 4), dtype=torch.float32, pin_memory=True)
+    pipe = HostPipeline(net, chunk=1 << 23, device=dev, mode=engine)
+    for _ in range(3):
+        pipe.run(coords_host, out_host)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for _ in range(args.steps):
+        pipe.run(coords_host, out_host)   # returns after the last D2H has landed
+    g1.record()
+    torch.cuda.synchronize(dev)
+    ms_e2e = max(g0.elapsed_time(g1), (time.perf_counter() - t0) * 1e3) / args.steps
+    e2e_checksum = float(out_host[:: max(1, n // 4096), 0].double().sum())
+
+    # max over ranks
+    if world > 1:
+        tt = torch.tensor([ms_step, ms_kernel, ms_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_step, ms_kernel, ms_e2e = [float(v) for v in tt.tolist()]
+
+    if rank == 0:
+        total_pts = world * n
+        value = total_pts / (ms_step / 1e3)
+        kernel_tflops = n * FLOP_PER_POINT / (ms_kernel / 1e3) / 1e12
+        # the jet kernel runs ~0.5-1 s per launch under the power cap: the sustained cuBLAS figure is the fair peak
+        peak = peaks["tf_sustained"]
+        iso = bench_isocontours(dev, peaks)
+        cores = os.cpu_count() or 1
+        cpu_pps, cpu_dt = cpu_port_points_per_s(262144, 2, cores)
+        line = {
+            "metric": "siren_value_grad_points_per_s", "value": value, "unit": "points/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f16x3-split operands, f32 accumulate" if engine == "tc_precise" else engine,
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "network": "3-256-256-256-256-1 sine, random init seed 2048",
+                       "grid": GRID_N, "points_per_gpu": n, "engine": engine,
+                       "l2_note": "inputs (1.6 GB coords) and outputs (2.1 GB) per step exceed the 126 MB L2",
+                       "parallelism": f"dp{world}: points sharded, weights replicated, one all-gather" if world > 1 else "single GPU"},
+            "e2e": {"value": total_pts / (ms_e2e / 1e3), "unit": "points/s", "h2d_bytes_per_step": n * 12,
+                    "d2h_bytes_per_step": n * 16, "ms_per_step": ms_e2e, "api": "inf3dp.HostPipeline.run(pinned coords, pinned out)",
+                    "checksum": e2e_checksum},
+            "gpu_launches": launches_per_step * args.steps,
+            "roofline": {"bound": "tensor", "achieved": kernel_tflops, "peak": peak, "unit": "TFLOP/s",
+                         "frac": kernel_tflops / peak, "traffic": None, "kernel": "siren_tc_kernel<1,precise>" if engine == "tc_precise" else engine,
+                         "kernel_ms": ms_kernel, "flop_per_point": FLOP_PER_POINT, "peak_kind": "bf16_tflops_sustained",
+                         "peak_source": peaks["source"], "frac_of_burst_peak": kernel_tflops / peaks["tf_burst"],
+                         "executed_tensor_flop_per_point": 3 * 1_572_864 + 3 * 2 * 16 * 256 * 4 if engine == "tc_precise" else 1_572_864,
+                         "reverse_mode_equivalent_flop_per_point": 790_528},
+            "cpu_baseline": {"value": cpu_pps, "unit": "points/s", "cores": cores, "kind": "port",
+                             "sample": "262144 grid points, best of 2, oracle/siren_torch_port.field_query_with_grads (torch CPU)"},
+            "isocontour": iso,
+            "clocks": clocks,
+            "torch": torch.__version__,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

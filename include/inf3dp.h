@@ -69,6 +69,10 @@ int inf3dp_siren_pack_weights(const float* const* weights_host, const float* con
 int inf3dp_siren_jet(const void* packed, const float* x, int64_t n, int order, float* y, float* J, float* H,
                      int mode, inf3dp_stream_t stream);
 
+/* Unit normals: normals = grad / max(|grad|, eps), rows of 3 (torch.nn.functional.normalize as applied after
+ * field_query_with_grads, toolpath_utils.py:180-181).  In-place (normals == grad) is allowed. */
+int inf3dp_unit_normals(const float* grad, int64_t n, float eps, float* normals, inf3dp_stream_t stream);
+
 /* Curvature tail.  Replaces the per-point Python loop of diff_operators.py:167-220 (min_max_curvs_and_vectors)
  * and construct_tangent_basis (:280-298): grad [n,3], hess [n,3,3] -> kappa [n,2] (min,max), dirs [n,2,3]. */
 int inf3dp_principal_curvatures(const float* grad, const float* hess, int64_t n, float* kappa, float* dirs,

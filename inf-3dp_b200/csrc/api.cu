@@ -132,6 +132,18 @@ __global__ void principal_curvatures_kernel(const float* __restrict__ grad, cons
     }
 }
 
+// Unit normals from gradients: out = g / max(|g|, eps)  (torch.nn.functional.normalize semantics, the step the
+// reference applies after field_query_with_grads, e.g. toolpath_utils.py:180-181).  One thread per point.
+__global__ void unit_normals_kernel(const float* __restrict__ g, int64_t n, float eps, float* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float x = g[3 * i], y = g[3 * i + 1], z = g[3 * i + 2];
+    const float nrm = fmaxf(sqrtf(x * x + y * y + z * z), eps);
+    out[3 * i] = x / nrm;
+    out[3 * i + 1] = y / nrm;
+    out[3 * i + 2] = z / nrm;
+}
+
 }  // namespace inf3dp
 
 using namespace inf3dp;
@@ -230,6 +242,15 @@ int inf3dp_siren_jet(const void* packed, const float* x, int64_t n, int order, f
             set_error("siren_jet: unknown mode %d", mode);
             return INF3DP_EINVAL;
     }
+}
+
+int inf3dp_unit_normals(const float* grad, int64_t n, float eps, float* normals, inf3dp_stream_t stream) {
+    INF3DP_CHECK_ARG(n >= 0, "unit_normals: negative n");
+    if (n == 0) return INF3DP_OK;
+    INF3DP_CHECK_ARG(grad && normals, "unit_normals: null pointer");
+    unit_normals_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(grad, n, eps, normals);
+    INF3DP_LAUNCH_CHECK("unit_normals_kernel");
+    return INF3DP_OK;
 }
 
 int inf3dp_principal_curvatures(const float* grad, const float* hess, int64_t n, float* kappa, float* dirs,

@@ -112,6 +112,18 @@ def principal_curvatures(grad_y, hess):
     return kappa, dirs
 
 
+def unit_normals(grads, eps=1e-12, out=None):
+    """F.normalize(grads, dim=-1) for [..., 3] gradients on the device (toolpath_utils.py:180-181)."""
+    if not grads.is_cuda:
+        raise RuntimeError("inf3dp: unit_normals needs CUDA tensors (no CPU fallback)")
+    g = grads.detach().to(torch.float32).contiguous()
+    out = torch.empty_like(g) if out is None else out
+    with torch.cuda.device(g.device):
+        _lib.check(_lib.lib().inf3dp_unit_normals(_lib.ptr(g), g.numel() // 3, float(eps), _lib.ptr(out),
+                                                   _lib.stream_ptr(g.device)))
+    return out
+
+
 def min_max_curvs_and_vectors(f, x_temp):
     """diff_operators.py:167-220: f maps [N,3] coords to the {'model_in','model_out'} dict of a fused network."""
     x_temp = x_temp.clone().detach().requires_grad_(True)

@@ -47,6 +47,24 @@ def field_query_with_grads(decoder, coords, max_batch=1 << 22, mode=None):
     return fields, grads
 
 
+def gen_voxel_queries(N, cube_size=1.0, device=None):
+    """The reference's query grid (sdf_meshing.py:46-65) built on `device`, bit-identical to the reference's CPU
+    result INCLUDING its true-division shear: y and x indices are the float32 values (i / N) % N and
+    ((i / N) / N) % N, not integers.  Returns (samples [N^3, 3] f32, origin, voxel_size)."""
+    voxel_size = cube_size * 2.0 / (N - 1)
+    idx = torch.arange(0, N ** 3, 1, dtype=torch.long, device=device)
+    samples = torch.zeros(N ** 3, 3, device=device)
+    samples[:, 2] = idx % N
+    q1 = idx / N            # true division on a LongTensor -> float32, as in the reference
+    samples[:, 1] = q1 % N
+    samples[:, 0] = (q1 / N) % N
+    del idx, q1
+    samples[:, 0] = (samples[:, 0] * voxel_size) + (-cube_size)
+    samples[:, 1] = (samples[:, 1] * voxel_size) + (-cube_size)
+    samples[:, 2] = (samples[:, 2] * voxel_size) + (-cube_size)
+    return samples, (-cube_size, -cube_size, -cube_size), voxel_size
+
+
 class HostPipeline:
     """Value+gradient queries for HOST-resident coordinates (the reference's calling pattern: CPU tensors in,
     CPU tensors out, utils.py:232-253) with copies overlapped with compute.
