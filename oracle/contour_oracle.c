@@ -216,16 +216,19 @@ int oracle_fields_intersection(const float* s, const float* l1, const float* l2,
     return 0;
 }
 
-/* Race-tolerant check of a (mask, pts) pair produced by ANY schedule of the reference kernel: a cell passes
- * if some voxel that hits it produces its point within `tol` (NaN matches NaN).  Returns the number of
- * failing cells: masked cells no candidate explains, plus cells whose mask disagrees with "some voxel hits". */
+/* Race-tolerant check of a (mask, pts) pair produced by ANY schedule of the reference kernel.  The reference
+ * writes the three coordinates of a cell with three plain stores (intersection.cu:216-218), so when several
+ * voxels hit one cell the result may even be TORN (x from one voxel, y/z from another): a cell passes if every
+ * coordinate equals, within `tol`, that coordinate of some voxel that hits the cell (NaN matches NaN).
+ * Returns the number of failing cells: cells with an unexplained coordinate, plus cells whose mask disagrees
+ * with "some voxel hits". */
 long oracle_intersection_unmatched(const float* s, const float* l1, const float* l2, const float* s_iso,
                                    const float* l1_iso, const float* l2_iso, const float* centers, int Dx, int Dy,
                                    int Dz, int Ns, int N1, int N2, const uint8_t* mask, const float* pts,
                                    float tol) {
     size_t cells = (size_t)Ns * N1 * N2;
     uint8_t* hit = (uint8_t*)calloc(cells, 1);
-    uint8_t* ok = (uint8_t*)calloc(cells, 1);
+    uint8_t* ok = (uint8_t*)calloc(cells, 1);   /* bit d set: coordinate d explained */
     if (!hit || !ok) { free(hit); free(ok); return -1; }
     const float vs = (float)(2.0 / (double)(float)Dx);
     for (int x = 0; x < Dx; ++x)
@@ -247,16 +250,13 @@ long oracle_intersection_unmatched(const float* s, const float* l1, const float*
                             if (si < smn || si > smx) continue;
                             size_t c = ((size_t)is * N1 + i1) * N2 + i2;
                             hit[c] = 1;
-                            if (ok[c]) continue;
+                            if (ok[c] == 7) continue;
                             float p[3];
                             voxel_cell_point(s + 8 * v, l1 + 8 * v, l2 + 8 * v, si, ai, bi, centers + 3 * v, vs, p);
-                            int good = 1;
                             for (int d = 0; d < 3; ++d) {
                                 float q = pts[3 * c + d];
-                                if (isnan(p[d]) && isnan(q)) continue;
-                                if (!(fabsf(p[d] - q) <= tol)) good = 0;
+                                if ((isnan(p[d]) && isnan(q)) || fabsf(p[d] - q) <= tol) ok[c] |= (uint8_t)(1 << d);
                             }
-                            if (good) ok[c] = 1;
                         }
                     }
                 }
@@ -264,7 +264,7 @@ long oracle_intersection_unmatched(const float* s, const float* l1, const float*
     long bad = 0;
     for (size_t c = 0; c < cells; ++c) {
         if ((mask[c] != 0) != (hit[c] != 0)) ++bad;
-        else if (hit[c] && !ok[c]) ++bad;
+        else if (hit[c] && ok[c] != 7) ++bad;
     }
     free(hit); free(ok);
     return bad;
