@@ -22,6 +22,7 @@
 // Output contract (identical to the reference): contours_merged [K,F,3] zero padded, per isovalue the row stream
 // [seed.p1, far endpoint of each chained segment ...] (-1e9 row) ... ; contour_nums [K].
 #include <mutex>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -44,6 +45,7 @@ struct ContourWs {
     float* seg_pts;      // [cap][6]
     int* seg_slot;       // [cap][2] hash slot of each endpoint
     int* seg_link;       // [cap][2] partner endpoint id (2*seg+side) or -1
+    int* seg_order;      // [2*cap] row -> endpoint id (or -2 separator), per isovalue at 2*seg_offset
     unsigned char* used; // [cap]
     unsigned long long* hkeys;  // [hcap]
     int* hvals;          // [hcap][2]
@@ -86,6 +88,7 @@ ContourWs carve(void* base, int K, int cap) {
     w.seg_pts = (float*)(b + take((size_t)w.cap * 24));
     w.seg_slot = (int*)(b + take((size_t)w.cap * 8));
     w.seg_link = (int*)(b + take((size_t)w.cap * 8));
+    w.seg_order = (int*)(b + take((size_t)w.cap * 8));
     w.used = (unsigned char*)(b + take((size_t)w.cap));
     w.hkeys = (unsigned long long*)(b + take((size_t)w.hcap * 8));
     w.hvals = (int*)(b + take((size_t)w.hcap * 8));
@@ -313,11 +316,23 @@ __global__ void contour_link_kernel(ContourWs w) {
     }
 }
 
-// walk: one CTA per isovalue.
-__global__ void __launch_bounds__(128)
+// walk: one CTA per isovalue.  The isovalue's partner links are copied into shared memory (local endpoint ids) and
+// one thread walks the chain with ONE dependent shared-memory load per step.  No `used` lookup sits on the chain:
+// a walk can only ever run into a consumed segment through the back side (p1) of a SEED -- a non-seed segment is
+// entered from the segment before it and left into the segment after it, both consumed by the same walk -- so
+// seeding kills the one link that leads into the seed's p1 (link[partner(seed.p1)] = -1).  A closed loop coming
+// back to its seed, or a later walk reaching an earlier seed from behind, then reads -1 and stops: exactly the
+// reference's "no unused segment within the merge radius" exit (isocontours.cu:157-203).
+constexpr int kWalkThreads = 256;
+constexpr int kWalkSmemSegs = 6144;  // segments per isovalue walked entirely in shared memory (links + order + used)
+constexpr int kWalkSmemBytes = kWalkSmemSegs * (8 + 8 + 4);
+
+__global__ void __launch_bounds__(kWalkThreads)
 contour_walk_kernel(int nF, ContourWs w, float* __restrict__ merged, int* __restrict__ nums) {
+    extern __shared__ int s_dyn[];
     const int k = blockIdx.x;
-    __shared__ int s_best[4];
+    __shared__ int s_face[kWalkThreads / 32];
+    __shared__ int s_best[kWalkThreads / 32];
     __shared__ int s_seed;
     const bool overflow = w.hdr[0] != 0;
     const int S = overflow ? 0 : w.seg_count[k];
@@ -326,76 +341,90 @@ contour_walk_kernel(int nF, ContourWs w, float* __restrict__ merged, int* __rest
         if (threadIdx.x == 0) { nums[k] = 0; w.rows_used[k] = 0; }
         return;
     }
-    // pull this isovalue's working set through L1 (each line is touched once by the walker afterwards)
-    {
-        int acc = 0;
-        const int* lk = w.seg_link + 2ll * off;
-        for (int i = threadIdx.x * 32; i < 2 * S; i += blockDim.x * 32) acc ^= __ldca(lk + i);
-        const float* pt = w.seg_pts + 6ll * off;
-        for (int i = threadIdx.x * 32; i < 6 * S; i += blockDim.x * 32) acc ^= __float_as_int(__ldca(pt + i));
-        if (acc == 0x7fffffff) s_best[0] = acc;  // keep the loads alive
+    // Working set of the chain walk: partner links (local endpoint ids), the row order being recorded and the
+    // per-segment consumed flags.  In shared memory when the isovalue fits (no global traffic on the chain, which
+    // matters because the zero fill saturates HBM concurrently), in the workspace otherwise.
+    int* lk;
+    int* order;
+    int* used;
+    const bool in_smem = S <= kWalkSmemSegs;
+    if (in_smem) {
+        lk = s_dyn;
+        order = s_dyn + 2 * kWalkSmemSegs;
+        used = s_dyn + 4 * kWalkSmemSegs;
+    } else {
+        lk = w.seg_link + 2ll * off;
+        order = w.seg_order + 2ll * off;
+        used = w.seg_slot + 2ll * off;  // the hash-slot array is dead after `link`: reuse it as int flags
     }
+    for (int i = threadIdx.x; i < 2 * S; i += blockDim.x) {
+        const int g = w.seg_link[2ll * off + i];
+        lk[i] = g < 0 ? -1 : g - 2 * off;  // all partners belong to the same isovalue
+    }
+    for (int i = threadIdx.x; i < S; i += blockDim.x) used[i] = 0;
+    const float* pts = w.seg_pts + 6ll * off;       // [S][2][3] == flat [endpoint][3]; rows <= S + C <= 2S
     float* out = merged + (size_t)k * nF * 3;
+    __shared__ int s_rows;
     int row = 0, contours = 0;
+    __syncthreads();
+    // phase 1: one thread records the row order (endpoint ids); nothing but shared-memory loads on its chain
     while (true) {
-        // lowest face id among unused segments (ascending-face seed order)
+        // lowest face id among unused segments (ascending-face seed order); face ids are unique per isovalue
         int best_face = 0x7fffffff, best_seg = -1;
         for (int i = threadIdx.x; i < S; i += blockDim.x) {
-            if (!w.used[off + i]) {
+            if (!used[i]) {
                 const int f = w.seg_face[off + i];
                 if (f < best_face) { best_face = f; best_seg = i; }
             }
         }
-        // face ids are unique within an isovalue, so the min over faces identifies the segment
         for (int o = 16; o > 0; o >>= 1) {
             const int of = __shfl_xor_sync(0xffffffffu, best_face, o);
             const int os = __shfl_xor_sync(0xffffffffu, best_seg, o);
             if (of < best_face) { best_face = of; best_seg = os; }
         }
-        __shared__ int s_face[4];
         if ((threadIdx.x & 31) == 0) { s_face[threadIdx.x >> 5] = best_face; s_best[threadIdx.x >> 5] = best_seg; }
         __syncthreads();
         if (threadIdx.x == 0) {
             int bf = s_face[0], bs = s_best[0];
-            for (int i = 1; i < 4; ++i) if (s_face[i] < bf) { bf = s_face[i]; bs = s_best[i]; }
+            for (int i = 1; i < kWalkThreads / 32; ++i) if (s_face[i] < bf) { bf = s_face[i]; bs = s_best[i]; }
             s_seed = bs;
         }
         __syncthreads();
         const int seed = s_seed;
         if (seed < 0) break;
         if (threadIdx.x == 0) {
-            if (contours > 0) {  // isocontours.cu:135-140
-                if (row < nF) { out[3ll * row] = -1e9f; out[3ll * row + 1] = -1e9f; out[3ll * row + 2] = -1e9f; }
-                ++row;
-            }
-            const float* sp = w.seg_pts + 6ll * (off + seed);
-            if (row < nF) { out[3ll * row] = sp[0]; out[3ll * row + 1] = sp[1]; out[3ll * row + 2] = sp[2]; }
-            ++row;
-            w.used[off + seed] = 1;
+            if (contours > 0) order[row++] = -2;      // separator between loops (isocontours.cu:135-140)
+            order[row++] = 2 * seed;                   // seed.p1 (isocontours.cu:143-146)
+            used[seed] = 1;
             ++contours;
-            int cur_end = 2 * (off + seed) + 1;  // tail = seed.p2 (isocontours.cu:151-153)
+            // links into the seed become dead ends: the loop closes when the walk comes back to it
+            const int z = lk[2 * seed];
+            if (z >= 0) lk[z] = -1;
+            int cur_end = 2 * seed + 1;                // tail = seed.p2 (isocontours.cu:151-153)
             while (true) {
-                const int partner = w.seg_link[cur_end];
-                if (partner < 0) break;
-                const int ns = partner >> 1;
-                if (w.used[ns]) break;
-                const int far = (partner & 1) ^ 1;
-                const float* q = w.seg_pts + 6ll * ns + 3 * far;
-                if (row < nF) { out[3ll * row] = q[0]; out[3ll * row + 1] = q[1]; out[3ll * row + 2] = q[2]; }
-                ++row;
-                w.used[ns] = 1;
-                cur_end = 2 * ns + far;
+                const int y = lk[cur_end];             // entry endpoint of the next segment (the only dependent load)
+                if (y < 0) break;
+                cur_end = y ^ 1;                       // leave through its other endpoint ...
+                order[row++] = cur_end;                // ... whose point is the emitted row
+                used[y >> 1] = 1;
             }
         }
-        __syncthreads();
+        __syncthreads();  // `used` written by thread 0 is visible to the next seed search
     }
     if (threadIdx.x == 0) {
-        if (contours > 0) {  // isocontours.cu:205-210
-            if (row < nF) { out[3ll * row] = -1e9f; out[3ll * row + 1] = -1e9f; out[3ll * row + 2] = -1e9f; }
-            ++row;
-        }
+        if (contours > 0) order[row++] = -2;           // trailing separator (isocontours.cu:205-210)
         nums[k] = contours;
+        s_rows = row;
         w.rows_used[k] = min(row, nF);
+    }
+    __syncthreads();
+    // phase 2: all threads gather the points and write the row stream
+    const int rows = min(s_rows, nF);
+    for (int r = threadIdx.x; r < rows; r += blockDim.x) {
+        const int e = order[r];
+        float a = -1e9f, b = -1e9f, c = -1e9f;
+        if (e >= 0) { const float* q = pts + 3ll * e; a = q[0]; b = q[1]; c = q[2]; }
+        out[3ll * r] = a; out[3ll * r + 1] = b; out[3ll * r + 2] = c;
     }
 }
 
@@ -404,29 +433,31 @@ contour_walk_kernel(int nF, ContourWs w, float* __restrict__ merged, int* __rest
 template <int PHASE>
 __global__ void __launch_bounds__(256)
 contour_fill_kernel(int nF, int K, ContourWs w, float* __restrict__ merged) {
-    const int k = blockIdx.y;
     const bool overflow = w.hdr[0] != 0;
-    const long long S = overflow ? 0 : w.seg_count[k];
-    const long long split = min(2 * S, (long long)nF);
-    long long r0, r1;
-    if (PHASE == 0) { r0 = split; r1 = nF; } else { r0 = w.rows_used[k]; r1 = split; }
-    if (r0 >= r1) return;
-    float* base = merged + (size_t)k * nF * 3;
-    long long e0 = 3 * r0, e1 = 3 * r1;  // float range inside this isovalue's slab
-    // align the body to 16 bytes (the slab start is only 4-byte aligned in general)
-    const uintptr_t addr0 = reinterpret_cast<uintptr_t>(base + e0);
-    long long head = ((16 - (addr0 & 15)) & 15) >> 2;
-    if (head > e1 - e0) head = e1 - e0;
-    const long long body0 = e0 + head;
-    const long long nvec = (e1 - body0) >> 2;
-    const long long tail0 = body0 + 4 * nvec;
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long nth = (long long)gridDim.x * blockDim.x;
-    if (tid < head) base[e0 + tid] = 0.f;
-    if (tid < e1 - tail0) base[tail0 + tid] = 0.f;
-    float4* vb = reinterpret_cast<float4*>(base + body0);
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (long long i = tid; i < nvec; i += nth) __stcs(vb + i, z);
+    for (int k = blockIdx.y; k < K; k += gridDim.y) {
+        const long long S = overflow ? 0 : w.seg_count[k];
+        const long long split = min(2 * S, (long long)nF);
+        long long r0, r1;
+        if (PHASE == 0) { r0 = split; r1 = nF; } else { r0 = w.rows_used[k]; r1 = split; }
+        if (r0 >= r1) continue;
+        float* base = merged + (size_t)k * nF * 3;
+        const long long e0 = 3 * r0, e1 = 3 * r1;  // float range inside this isovalue's slab
+        // align the body to 16 bytes (the slab start is only 4-byte aligned in general)
+        const uintptr_t addr0 = reinterpret_cast<uintptr_t>(base + e0);
+        long long head = ((16 - (addr0 & 15)) & 15) >> 2;
+        if (head > e1 - e0) head = e1 - e0;
+        const long long body0 = e0 + head;
+        const long long nvec = (e1 - body0) >> 2;
+        const long long tail0 = body0 + 4 * nvec;
+        if (tid < head) base[e0 + tid] = 0.f;
+        if (tid < e1 - tail0) base[tail0 + tid] = 0.f;
+        float4* vb = reinterpret_cast<float4*>(base + body0);
+#pragma unroll 4
+        for (long long i = tid; i < nvec; i += nth) __stcs(vb + i, z);
+    }
 }
 
 static cudaStream_t g_side[64] = {nullptr};
@@ -438,7 +469,14 @@ int get_side_stream(cudaStream_t* out) {
     INF3DP_CUDA(cudaGetDevice(&dev));
     INF3DP_CHECK_ARG(dev >= 0 && dev < 64, "device index %d out of range", dev);
     std::lock_guard<std::mutex> lk(g_mu);
-    if (g_side[dev] == nullptr) INF3DP_CUDA(cudaStreamCreateWithFlags(&g_side[dev], cudaStreamNonBlocking));
+    if (g_side[dev] == nullptr) {
+        // HIGHEST priority: the latency-bound chain (hash/link/walk) runs here while the bulk zero fill occupies the
+        // caller's stream; the block scheduler only lets a later kernel overtake the pending blocks of an earlier one
+        // when its stream has a higher priority (caller streams -- torch's default stream -- have the lowest)
+        int least = 0, greatest = 0;
+        INF3DP_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        INF3DP_CUDA(cudaStreamCreateWithPriority(&g_side[dev], cudaStreamNonBlocking, greatest));
+    }
     *out = g_side[dev];
     return INF3DP_OK;
 }
@@ -493,6 +531,12 @@ int inf3dp_extract_isocontours(const float* V, const int32_t* F, const float* fi
     cudaStream_t side;
     int rc = get_side_stream(&side);
     if (rc != INF3DP_OK) return rc;
+    // developer instrumentation (INF3DP_CONTOUR_DEBUG=1): per-phase CUDA-event timeline on both streams
+    static const bool debug = getenv("INF3DP_CONTOUR_DEBUG") != nullptr;
+    cudaEvent_t dbg_ev[8] = {nullptr};
+    if (debug) for (int i = 0; i < 8; ++i) cudaEventCreate(&dbg_ev[i]);
+    auto mark = [&](int i, cudaStream_t s_) { if (debug) cudaEventRecord(dbg_ev[i], s_); };
+    mark(0, st);
 
     contour_prep_kernel<<<1, 1024, 0, st>>>(iso, K, w);
     INF3DP_LAUNCH_CHECK("contour_prep_kernel");
@@ -505,43 +549,64 @@ int inf3dp_extract_isocontours(const float* V, const int32_t* F, const float* fi
     contour_scan_kernel<<<1, 1024, 0, st>>>(K, w);
     INF3DP_LAUNCH_CHECK("contour_scan_kernel");
 
-    // fork: bulk zero fill on the side stream while hash/link/walk run on the caller's stream
+    // fork: the chain (hash/link/walk) goes to the high-priority helper stream, the bulk zero fill stays on the
+    // caller's stream; join before the tail fill (which needs the row counts the walk produced)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     INF3DP_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
     INF3DP_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
     INF3DP_CUDA(cudaEventRecord(ev_fork, st));
+    mark(1, st);
     INF3DP_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
     const int sms = num_sms();
     if (nF > 0) {
+        contour_hash_clear_kernel<<<sms * 4, 256, 0, side>>>(w);
+        INF3DP_LAUNCH_CHECK("contour_hash_clear_kernel");
+        contour_faces_kernel<true><<<fblocks, kFaceThreads, fsmem, side>>>(V, F, fields, nV, nF, K, w);
+        INF3DP_LAUNCH_CHECK("contour_faces_kernel<emit>");
+        mark(4, side);
+        contour_link_kernel<<<sms * 4, 256, 0, side>>>(w);
+        INF3DP_LAUNCH_CHECK("contour_link_kernel");
+        mark(5, side);
+    }
+    INF3DP_CUDA(cudaFuncSetAttribute(contour_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     kWalkSmemBytes));
+    contour_walk_kernel<<<K, kWalkThreads, kWalkSmemBytes, side>>>(nF, w, merged, nums);
+    INF3DP_LAUNCH_CHECK("contour_walk_kernel");
+    INF3DP_CUDA(cudaEventRecord(ev_join, side));
+    mark(6, side);
+
+    mark(2, st);
+    if (nF > 0) {
+        // Many SHORT blocks (each thread streams ~16 float4 stores): SM slots free up continuously, so the
+        // higher-priority chain kernels on the helper stream are dispatched between them.  (Measured alternatives:
+        // a persistent 2-CTA/SM fill cannot keep enough stores in flight -- 3.8 TB/s instead of 6.1 TB/s.)
         const long long per_iso_vec = (3ll * nF) / 4 + 1;
         long long gxl = per_iso_vec / 4096;
         if (gxl < 1) gxl = 1;
-        if (gxl > 64) gxl = 64;
-        const int gx = (int)gxl;  // >= 16 float4 per thread
-        dim3 grid(gx, K);
-        contour_fill_kernel<0><<<grid, 256, 0, side>>>(nF, K, w, merged);
+        if (gxl > 256) gxl = 256;
+        dim3 grid((int)gxl, K);
+        contour_fill_kernel<0><<<grid, 256, 0, st>>>(nF, K, w, merged);
         INF3DP_LAUNCH_CHECK("contour_fill_kernel<0>");
     }
-    INF3DP_CUDA(cudaEventRecord(ev_join, side));
-
-    if (nF > 0) {
-        contour_hash_clear_kernel<<<sms * 4, 256, 0, st>>>(w);
-        INF3DP_LAUNCH_CHECK("contour_hash_clear_kernel");
-        contour_faces_kernel<true><<<fblocks, kFaceThreads, fsmem, st>>>(V, F, fields, nV, nF, K, w);
-        INF3DP_LAUNCH_CHECK("contour_faces_kernel<emit>");
-        contour_link_kernel<<<sms * 4, 256, 0, st>>>(w);
-        INF3DP_LAUNCH_CHECK("contour_link_kernel");
-    }
-    contour_walk_kernel<<<K, 128, 0, st>>>(nF, w, merged, nums);
-    INF3DP_LAUNCH_CHECK("contour_walk_kernel");
+    mark(3, st);
+    INF3DP_CUDA(cudaStreamWaitEvent(st, ev_join, 0));  // join
     if (nF > 0) {
         dim3 grid(8, K);
         contour_fill_kernel<1><<<grid, 256, 0, st>>>(nF, K, w, merged);
         INF3DP_LAUNCH_CHECK("contour_fill_kernel<1>");
     }
-    INF3DP_CUDA(cudaStreamWaitEvent(st, ev_join, 0));  // join
+    mark(7, st);
     INF3DP_CUDA(cudaEventDestroy(ev_fork));
     INF3DP_CUDA(cudaEventDestroy(ev_join));
+    if (debug) {
+        cudaStreamSynchronize(st);
+        float t[8] = {0};
+        for (int i = 1; i < 8; ++i) cudaEventElapsedTime(&t[i], dbg_ev[0], dbg_ev[i]);
+        fprintf(stderr, "[inf3dp contour debug] us since start: fork %.0f | caller stream: fill start %.0f end %.0f | chain stream: emit end %.0f "
+                        "link end %.0f walk end %.0f | tail fill end %.0f\n", t[1] * 1e3, t[2] * 1e3, t[3] * 1e3, t[4] * 1e3,
+                t[5] * 1e3, t[6] * 1e3, t[7] * 1e3);
+        for (int i = 0; i < 8; ++i) cudaEventDestroy(dbg_ev[i]);
+    }
     return INF3DP_OK;
 }
 

@@ -17,7 +17,7 @@ def timeit(fn, iters=5, warm=2):
 
 torch.manual_seed(2048)
 net = inf3dp.SingleBVPNet(type="sine", in_features=3).cuda()
-engines = sys.argv[1].split(",") if len(sys.argv) > 1 else ["simt"]
+engines = [e for e in (sys.argv[1].split(",") if len(sys.argv) > 1 else ["simt"]) if e != "none"]
 n = 1 << 22
 x = (torch.rand(n, 3, device="cuda") * 2 - 1)
 for eng in engines:
