@@ -56,7 +56,7 @@ constexpr uint32_t kSmemOutImg = kStages * kRingStageBytes;          // 196608
 constexpr uint32_t kSmemBias = kSmemOutImg + 16384;                  // 212992
 constexpr uint32_t kSmemW0 = kSmemBias + 6144;                       // 219136
 constexpr uint32_t kSmemB0 = kSmemW0 + 4096;                         // 223232
-constexpr uint32_t kSmemMisc = kSmemB0 + 1024;                       // 224256: inv_scale[4], b4[8]
+constexpr uint32_t kSmemMisc = kSmemB0 + 2048;                       // inv_scale[4], b4[8]   (b0 table is [256][2])
 constexpr uint32_t kSmemBars = kSmemMisc + 64;                       // 224320
 constexpr int kBarWFull = 0, kBarWEmpty = kStages, kBarAReady = 2 * kStages, kBarDFull = 2 * kStages + 4,
               kBarOutImg = 2 * kStages + 5, kNumBars = 2 * kStages + 6;
@@ -193,20 +193,12 @@ __device__ __forceinline__ float sin_mufu(float x) {
     asm("sin.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
-// Layer 0 arguments reach |z| ~ 50 rad (30 * (|W0 x| + |b0|)).  MUFU.SIN reduces modulo one revolution itself
-// after the x * 1/(2 pi) scaling that sin.approx performs in FP32, so the absolute phase error grows like
-// |z| * 2^-24 * 2 pi ~ 2e-5 rad at |z| = 50; two-constant Cody-Waite reduction first keeps it at the 1e-6 level
-// for ~4 more FP32 instructions per feature.  PRECISE keeps the reduction, FAST drops it.
-template <bool PRECISE>
-__device__ __forceinline__ float sin_layer0(float x) {
-    if (PRECISE) {
-        const float k = rintf(x * 0.15915494309189535f);
-        float r = fmaf(-k, 6.28318548202514648f, x);        // 2*pi rounded to FP32
-        r = fmaf(-k, -1.74845553146951715e-7f, r);           // 2*pi - fl(2*pi)
-        return sin_mufu(r);
-    }
-    return sin_mufu(x);
-}
+// Layer 0 arguments reach |z| ~ 50 rad (30 * (|W0 x| + |b0|)).  sin.approx scales by 1/(2 pi) in FP32 (round toward
+// zero) and MUFU.SIN reduces modulo one revolution itself, so the absolute phase error is at most one FP32 ulp of
+// z / (2 pi) ~ 2^-20 revolutions = 6e-6 rad at |z| = 50 -- three orders of magnitude inside the 0.1 degree / 3.46e-4
+// parity budget (measured end to end in tests/test_gpu_siren.py), which is why no explicit Cody-Waite reduction
+// (4 more FP32 instructions per feature) is spent here.
+__device__ __forceinline__ float sin_layer0(float x) { return sin_mufu(x); }
 
 // Split two FP32 values into packed FP16 hi and lo words (value 0 in the low half = lower feature index).
 template <bool PRECISE>
@@ -258,10 +250,11 @@ siren_tc_kernel(const char* __restrict__ packed, SirenHeader h, const float* __r
         for (int i = tid; i < 3 * 256 * 2; i += kThreadsTc) s_bias[i] = g_bias[i];
         float* s_w0 = reinterpret_cast<float*>(sptr + kSmemW0);
         const float* g_w0 = reinterpret_cast<const float*>(packed + h.off_w0);
-        for (int i = tid; i < 256 * 4; i += kThreadsTc) s_w0[i] = g_w0[i];
+        // [f] = (w_x, w_y, w_z, 1): lane c reads its layer-0 tangent factor as element (c + 3) & 3 -- no branches
+        for (int i = tid; i < 256 * 4; i += kThreadsTc) s_w0[i] = (i & 3) == 3 ? 1.f : g_w0[i];
         float* s_b0 = reinterpret_cast<float*>(sptr + kSmemB0);
         const float* g_b0 = reinterpret_cast<const float*>(packed + h.off_b0);
-        for (int i = tid; i < 256; i += kThreadsTc) s_b0[i] = g_b0[i];
+        for (int i = tid; i < 256; i += kThreadsTc) { s_b0[2 * i] = g_b0[i]; s_b0[2 * i + 1] = g_b0[i] + kHalfPi; }
         float* s_misc = reinterpret_cast<float*>(sptr + kSmemMisc);
         if (tid < 4) s_misc[tid] = reinterpret_cast<const float*>(tc + kTcOffScales)[tid];
         if (tid >= 4 && tid < 12) s_misc[tid] = reinterpret_cast<const float*>(tc + kTcOffB4)[tid - 4];
@@ -394,9 +387,9 @@ siren_tc_kernel(const char* __restrict__ packed, SirenHeader h, const float* __r
         const int qbase = lane & ~3;                         // lane holding this point's value row
         const float* s_bias = reinterpret_cast<const float*>(sptr + kSmemBias) + (c != 0 ? 1 : 0);
         const float4* s_w0 = reinterpret_cast<const float4*>(sptr + kSmemW0);
-        const float* s_b0 = reinterpret_cast<const float*>(sptr + kSmemB0);
+        const float* s_w0m = reinterpret_cast<const float*>(sptr + kSmemW0) + ((c + 3) & 3);  // 1, w_x, w_y, w_z
+        const float* s_b0 = reinterpret_cast<const float*>(sptr + kSmemB0) + (c != 0 ? 1 : 0); // b0 (+ pi/2)
         const float* s_misc = reinterpret_cast<const float*>(sptr + kSmemMisc);
-        const float phase0 = c != 0 ? kHalfPi : 0.f;
         uint32_t dphase = 0;
         unsigned long long wait_d = 0;
         unsigned long long* pd = (dbg && lane == 0) ? &wait_d : nullptr;
@@ -420,12 +413,10 @@ siren_tc_kernel(const char* __restrict__ packed, SirenHeader h, const float* __r
                     for (int u = 0; u < 2; ++u) {
                         const int f = 16 * m + i + u;
                         const float4 w = s_w0[f];
-                        float z = fmaf(w.x, px, s_b0[f]);
+                        float z = fmaf(w.x, px, s_b0[2 * f]);   // b0' (+ pi/2 on tangent rows: cos = sin(. + pi/2))
                         z = fmaf(w.y, py, z);
                         z = fmaf(w.z, pz, z);
-                        const float s = sin_layer0<PRECISE>(z + phase0);
-                        const float mult = c == 0 ? 1.f : (c == 1 ? w.x : (c == 2 ? w.y : w.z));
-                        r2[u] = s * mult;
+                        r2[u] = sin_layer0(z) * s_w0m[4 * f];
                     }
                     split_pack<PRECISE>(r2[0], r2[1], o[i >> 1], o[8 + (i >> 1)]);
                 }
