@@ -236,7 +236,7 @@ int inf3dp_siren_jet(const void* packed, const float* x, int64_t n, int order, f
         case INF3DP_MODE_TC_PRECISE:
         case INF3DP_MODE_TC_FAST:
             INF3DP_CHECK_ARG(tc_capable, "siren_jet: tensor-core engine needs sine, in=3, hidden=256, 3 hidden layers, "
-                             "out<=8 and order<=1");
+                             "out<=4 and order<=1");
             return siren_tc_launch(packed, h, x, n, order, y, J, mode == INF3DP_MODE_TC_PRECISE, st);
         default:
             set_error("siren_jet: unknown mode %d", mode);

@@ -102,7 +102,7 @@ inline SirenLayout siren_layout(int in_features, int hidden, int L, int out, int
     l.off_wout = o; o += (size_t)kMaxOut * hidden * 4;
     l.off_bout = o; o += (size_t)kMaxOut * 4;
     o = align_up(o, 1024);
-    l.tc_ok = (in_features == 3 && hidden == kHidden && L == 3 && out <= 8 && activation == INF3DP_ACT_SINE);
+    l.tc_ok = (in_features == 3 && hidden == kHidden && L == 3 && out <= 4 && activation == INF3DP_ACT_SINE);
     l.off_tc = o;
     // the TC section is always reserved for in=3/L=3 so the blob size does not depend on the activation
     if (in_features == 3 && hidden == kHidden && L == 3 && out <= 8) o += siren_tc_section_bytes();

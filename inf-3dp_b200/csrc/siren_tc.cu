@@ -52,14 +52,15 @@ constexpr size_t kTcSectionBytes = kTcOffHidImg + 3 * kLayerImgBytes;
 constexpr int kStages = 3;                 // ring stages of 4 K-steps (2 consecutive 32 KB image stages)
 constexpr uint32_t kRingStageBytes = 2 * kStageBytes;
 constexpr uint32_t kSmemRing = 0;
-constexpr uint32_t kSmemOutImg = kStages * kRingStageBytes;          // 196608
-constexpr uint32_t kSmemBias = kSmemOutImg + 16384;                  // 212992
+constexpr uint32_t kSmemW4 = kStages * kRingStageBytes;              // 196608: f32 W4[4][256] (output layer)
+constexpr uint32_t kSmemPartial = kSmemW4 + 4096;                    // f32 partial[4 warp groups][4 outputs][128 rows]
+constexpr uint32_t kSmemBias = kSmemPartial + 8192;
 constexpr uint32_t kSmemW0 = kSmemBias + 6144;                       // 219136
 constexpr uint32_t kSmemB0 = kSmemW0 + 4096;                         // 223232
 constexpr uint32_t kSmemMisc = kSmemB0 + 2048;                       // inv_scale[4], b4[8]   (b0 table is [256][2])
 constexpr uint32_t kSmemBars = kSmemMisc + 64;                       // 224320
 constexpr int kBarWFull = 0, kBarWEmpty = kStages, kBarAReady = 2 * kStages, kBarDFull = 2 * kStages + 4,
-              kBarOutImg = 2 * kStages + 5, kNumBars = 2 * kStages + 6;
+              kNumBars = 2 * kStages + 5;
 constexpr uint32_t kSmemTmemPtr = kSmemBars + kNumBars * 8;
 constexpr uint32_t kSmemTotal = kSmemTmemPtr + 16;
 static_assert(kSmemTotal <= 232448 - 1024, "shared memory budget (1 KB reserved for base alignment)");
@@ -215,7 +216,7 @@ __device__ __forceinline__ void split_pack(float o0, float o1, uint32_t& hi, uin
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-template <int ORDER, bool PRECISE>
+template <int ORDER, bool PRECISE, int OUTC>
 __global__ void __launch_bounds__(kThreadsTc, 1)
 siren_tc_kernel(const char* __restrict__ packed, SirenHeader h, const float* __restrict__ x, int64_t n,
                 float* __restrict__ y, float* __restrict__ J, unsigned long long* __restrict__ dbg) {
@@ -241,7 +242,6 @@ siren_tc_kernel(const char* __restrict__ packed, SirenHeader h, const float* __r
         for (int s = 0; s < kStages; ++s) { mbar_init(bar(kBarWFull + s), 1); mbar_init(bar(kBarWEmpty + s), 1); }
         for (int r = 0; r < 4; ++r) mbar_init(bar(kBarAReady + r), kEpiWarps);  // round r: every warp's r-th slice
         mbar_init(bar(kBarDFull), 1);
-        mbar_init(bar(kBarOutImg), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     {   // small FP32 tables through the generic proxy (read by CUDA cores only)
@@ -255,6 +255,9 @@ siren_tc_kernel(const char* __restrict__ packed, SirenHeader h, const float* __r
         float* s_b0 = reinterpret_cast<float*>(sptr + kSmemB0);
         const float* g_b0 = reinterpret_cast<const float*>(packed + h.off_b0);
         for (int i = tid; i < 256; i += kThreadsTc) { s_b0[2 * i] = g_b0[i]; s_b0[2 * i + 1] = g_b0[i] + kHalfPi; }
+        float* s_w4 = reinterpret_cast<float*>(sptr + kSmemW4);
+        const float* g_w4 = reinterpret_cast<const float*>(packed + h.off_wout);  // [kMaxOut][256], rows >= out are 0
+        for (int i = tid; i < 4 * 256; i += kThreadsTc) s_w4[i] = g_w4[i];
         float* s_misc = reinterpret_cast<float*>(sptr + kSmemMisc);
         if (tid < 4) s_misc[tid] = reinterpret_cast<const float*>(tc + kTcOffScales)[tid];
         if (tid >= 4 && tid < 12) s_misc[tid] = reinterpret_cast<const float*>(tc + kTcOffB4)[tid - 4];
@@ -273,8 +276,6 @@ siren_tc_kernel(const char* __restrict__ packed, SirenHeader h, const float* __r
     if (warp == kProducerWarp) {
         // ================= weight producer =====================================================================
         if (lane == 0) {
-            mbar_expect_tx(bar(kBarOutImg), 16384);
-            bulk_g2s(sbase + kSmemOutImg, tc + kTcOffOutImg, 16384, bar(kBarOutImg));
             uint32_t stage = 0, phase = 0;
             for (int it = 0; it < my_tiles; ++it) {
                 for (int l = 0; l < 3; ++l) {
@@ -300,7 +301,6 @@ siren_tc_kernel(const char* __restrict__ packed, SirenHeader h, const float* __r
         // ================= MMA issuer ===========================================================================
         if (lane == 0) {
             constexpr uint32_t idesc256 = make_idesc(256);
-            constexpr uint32_t idesc16 = make_idesc(16);
             uint32_t stage = 0, wphase = 0;
             uint32_t aphase = 0;  // parity of the a_ready barriers (one completion per activation version)
             unsigned long long wait_a = 0, wait_w = 0, dbg_lag = 0;
@@ -308,7 +308,6 @@ siren_tc_kernel(const char* __restrict__ packed, SirenHeader h, const float* __r
             unsigned long long* pa = dbg ? &wait_a : nullptr;
             unsigned long long* pw = dbg ? &wait_w : nullptr;
             const long long t_begin = clock64();
-            mbar_wait(bar(kBarOutImg), 0);
             for (int it = 0; it < my_tiles; ++it) {
                 // hidden layers 1..3: A alternates P,Q,P ; D alternates Q,P,Q
                 for (int l = 0; l < 3; ++l) {
@@ -345,28 +344,7 @@ siren_tc_kernel(const char* __restrict__ packed, SirenHeader h, const float* __r
                     dbg_dphase ^= 1u;
                     aphase ^= 1u;
                 }
-                // output layer: A = activations of layer 3 (region Q), D = region P columns [0,16)
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    mbar_wait_timed(bar(kBarAReady + r), aphase, pa);
-                    tc_fence_after();
-#pragma unroll
-                    for (int tt = 0; tt < 4; ++tt) {
-                        const int t = 4 * r + tt;
-                        const uint32_t sb = sbase + kSmemOutImg + (uint32_t)t * 512u;
-                        const uint64_t bh = make_desc(sb, 256, 128);
-                        const uint32_t a_hi = regionQ + 16u * (uint32_t)t;
-                        mma_ts(regionP, a_hi, bh, idesc16, t > 0 ? 1u : 0u);
-                        if (PRECISE) {
-                            const uint64_t bl = make_desc(sb + 8192u, 256, 128);
-                            mma_ts(regionP, a_hi + 8u, bh, idesc16, 1u);
-                            mma_ts(regionP, a_hi, bl, idesc16, 1u);
-                        }
-                    }
-                }
-                tc_commit(bar(kBarDFull));
-                dbg_dphase ^= 1u;
-                aphase ^= 1u;
+                // (the linear output layer is folded into the last hidden layer's epilogue on the CUDA cores)
             }
             if (dbg && blockIdx.x == 0) {
                 dbg[4] = dbg_lag;
@@ -431,6 +409,12 @@ siren_tc_kernel(const char* __restrict__ packed, SirenHeader h, const float* __r
             // ---- hidden layers 1..3: D (FP32, region regD) -> activations in place --------------------------------
             // per-lane constants so that value and tangent rows run the same instruction stream:
             //   out = sin(z_value * inv + b (+ pi/2)) * (own * k1 + k0),  (k1,k0) = (0,1) value row, (inv,0) tangent row
+            // The LAST hidden layer does not write activations back: the linear output layer
+            //   y = W4 a3 + b4,   dy/dx_i = W4 da3_i        (exact FP32 weights)
+            // is accumulated on the CUDA cores while the activations are in registers.
+            float acc[OUTC];
+#pragma unroll
+            for (int o = 0; o < OUTC; ++o) acc[o] = 0.f;
 #pragma unroll 1
             for (int l = 0; l < 3; ++l) {
                 const uint32_t regD = (l & 1) ? regionP : regionQ;
@@ -452,52 +436,67 @@ siren_tc_kernel(const char* __restrict__ packed, SirenHeader h, const float* __r
 #pragma unroll
                     for (int i = 0; i < 16; ++i) cur[i] = __uint_as_float(v[i]);
                     if (mi < 3) TC_LD16(addr + 64u, v);  // prefetch the next slice (columns 16*(m+4)) under the math
-                    uint32_t o[16];
+                    if (l < 2) {
+                        uint32_t o[16];
 #pragma unroll
-                    for (int i = 0; i < 16; i += 2) {
-                        float r2[2];
+                        for (int i = 0; i < 16; i += 2) {
+                            float r2[2];
 #pragma unroll
-                        for (int u = 0; u < 2; ++u) {
-                            const int f = 16 * m + i + u;
-                            const float own = cur[i + u];
+                            for (int u = 0; u < 2; ++u) {
+                                const int f = 16 * m + i + u;
+                                const float own = cur[i + u];
+                                float zv = own;
+                                if (ORDER == 1) zv = __shfl_sync(0xffffffffu, own, qbase);
+                                const float arg = fmaf(zv, inv_scale, bl[2 * f]);  // + b' (+ pi/2 on tangent rows)
+                                const float sn = sin_mufu(arg);
+                                r2[u] = ORDER == 1 ? sn * fmaf(own, k1, k0) : sn;
+                            }
+                            split_pack<PRECISE>(r2[0], r2[1], o[i >> 1], o[8 + (i >> 1)]);
+                        }
+                        if (PRECISE) { TC_ST16(addr, o); } else { TC_ST8(addr, o); }
+                        tc_wait_st();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar(kBarAReady + mi));
+                    } else {
+                        const float* s_w4 = reinterpret_cast<const float*>(sptr + kSmemW4);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const int f = 16 * m + i;
+                            const float own = cur[i];
                             float zv = own;
                             if (ORDER == 1) zv = __shfl_sync(0xffffffffu, own, qbase);
-                            const float arg = fmaf(zv, inv_scale, bl[2 * f]);  // + b' (+ pi/2 on tangent rows)
-                            const float s = sin_mufu(arg);
-                            r2[u] = ORDER == 1 ? s * fmaf(own, k1, k0) : s;
+                            const float arg = fmaf(zv, inv_scale, bl[2 * f]);
+                            const float sn = sin_mufu(arg);
+                            const float val = ORDER == 1 ? sn * fmaf(own, k1, k0) : sn;
+#pragma unroll
+                            for (int o = 0; o < OUTC; ++o) acc[o] = fmaf(val, s_w4[o * 256 + f], acc[o]);
                         }
-                        split_pack<PRECISE>(r2[0], r2[1], o[i >> 1], o[8 + (i >> 1)]);
                     }
-                    if (PRECISE) { TC_ST16(addr, o); } else { TC_ST8(addr, o); }
-                    tc_wait_st();
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar(kBarAReady + mi));
                 }
             }
 
-            // ---- output layer: D_out in region P columns [0,16) ---------------------------------------------------
-            mbar_wait_warp(bar(kBarDFull), dphase, lane, pd);
-            dphase ^= 1u;
-            tc_fence_after();
-            if (grp == 0) {
-                uint32_t v[16];
-                TC_LD16(regionP + lane_off, v);
-                tc_wait_ld();
-                if (pvalid) {
-                    const float inv_out = s_misc[3];
+            // ---- output: sum the four feature-quarter partials of every row in a fixed order ------------------------
+            {
+                float* s_part = reinterpret_cast<float*>(sptr + kSmemPartial);
 #pragma unroll
-                    for (int o = 0; o < 8; ++o) {
+                for (int o = 0; o < OUTC; ++o) s_part[(grp * 4 + o) * 128 + row] = acc[o];
+                asm volatile("bar.sync 1, 512;" ::: "memory");  // the 16 epilogue warps only
+                if (grp == 0 && pvalid) {
+#pragma unroll
+                    for (int o = 0; o < OUTC; ++o) {
                         if (o < out_f) {
-                            const float val = __uint_as_float(v[o]) * inv_out;
+                            const float val = ((s_part[(0 * 4 + o) * 128 + row] + s_part[(1 * 4 + o) * 128 + row]) +
+                                               s_part[(2 * 4 + o) * 128 + row]) + s_part[(3 * 4 + o) * 128 + row];
                             if (c == 0) y[pt * out_f + o] = val + s_misc[4 + o];
                             else J[(pt * out_f + o) * 3 + (c - 1)] = val;
                         }
                     }
                 }
             }
-            // all epilogue warps passed d_full(out): the MMA warp has consumed every a_ready phase of this tile,
-            // so the next tile's layer 0 may overwrite region P
+            // Hazards into the next tile: region P (next layer-0 target) was last READ by the layer-3 MMAs, which
+            // completed before this warp passed d_full(3); region Q and s_part are only touched again behind
+            // a_ready / d_full barriers that need every epilogue warp to have left this point.
         }
         if (dbg && blockIdx.x == 0 && lane == 0) dbg[8 + warp] = wait_d;
     }
@@ -570,10 +569,10 @@ __global__ void tc_pack_out_kernel(const float* __restrict__ W, const float* __r
     *reinterpret_cast<__half*>(img + off + 8192) = lo;
 }
 
-template <int ORDER, bool PRECISE>
+template <int ORDER, bool PRECISE, int OUTC>
 int launch_tc(const void* packed, const SirenHeader& h, const float* x, int64_t n, float* y, float* J,
               cudaStream_t stream) {
-    auto kern = siren_tc_kernel<ORDER, PRECISE>;
+    auto kern = siren_tc_kernel<ORDER, PRECISE, OUTC>;
     const int smem = (int)kSmemTotal + 1024;
     INF3DP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     constexpr int kPts = ORDER == 1 ? 32 : 128;
@@ -628,10 +627,13 @@ int siren_tc_pack(const float* const* W, const float* const* b, float omega0, in
 int siren_tc_launch(const void* packed, const SirenHeader& h, const float* x, int64_t n, int order, float* y,
                     float* J, bool precise, cudaStream_t stream) {
     INF3DP_CHECK_ARG(h.tc_ok && h.off_tc != 0, "siren_tc: packed weights carry no tensor-core section");
-    if (order == 0) return precise ? launch_tc<0, true>(packed, h, x, n, y, J, stream)
-                                   : launch_tc<0, false>(packed, h, x, n, y, J, stream);
-    return precise ? launch_tc<1, true>(packed, h, x, n, y, J, stream)
-                   : launch_tc<1, false>(packed, h, x, n, y, J, stream);
+    const bool one = h.out_features == 1;
+    if (order == 0) {
+        if (precise) return one ? launch_tc<0, true, 1>(packed, h, x, n, y, J, stream) : launch_tc<0, true, 4>(packed, h, x, n, y, J, stream);
+        return one ? launch_tc<0, false, 1>(packed, h, x, n, y, J, stream) : launch_tc<0, false, 4>(packed, h, x, n, y, J, stream);
+    }
+    if (precise) return one ? launch_tc<1, true, 1>(packed, h, x, n, y, J, stream) : launch_tc<1, true, 4>(packed, h, x, n, y, J, stream);
+    return one ? launch_tc<1, false, 1>(packed, h, x, n, y, J, stream) : launch_tc<1, false, 4>(packed, h, x, n, y, J, stream);
 }
 
 }  // namespace inf3dp
