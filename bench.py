@@ -296,7 +296,11 @@ def run_ours(args):
         peak = peaks["tf_sustained"]
         iso = bench_isocontours(dev, peaks)
         cores = os.cpu_count() or 1
-        cpu_pps, cpu_dt = cpu_port_points_per_s(262144, 2, cores)
+        cpu_base = None
+        if world == 1:   # reported baseline: rank 0 at N=1 only (torchrun pins OMP threads to 1 for N>1)
+            cpu_pps, cpu_dt = cpu_port_points_per_s(262144, 2, cores)
+            cpu_base = {"value": cpu_pps, "unit": "points/s", "cores": cores, "kind": "port",
+                        "sample": "262144 grid points, best of 2, oracle/siren_torch_port.field_query_with_grads (torch CPU)"}
         line = {
             "metric": "siren_value_grad_points_per_s", "value": value, "unit": "points/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
@@ -311,13 +315,12 @@ def run_ours(args):
                     "checksum": e2e_checksum},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": {"bound": "tensor", "achieved": kernel_tflops, "peak": peak, "unit": "TFLOP/s",
-                         "frac": kernel_tflops / peak, "traffic": None, "kernel": "siren_tc_kernel<1,precise>" if engine == "tc_precise" else engine,
+                         "frac": kernel_tflops / peak, "traffic": None, "kernel": "siren_tc_kernel<ORDER=1,PRECISE,OUTC=1>" if engine == "tc_precise" else engine,
                          "kernel_ms": ms_kernel, "flop_per_point": FLOP_PER_POINT, "peak_kind": "bf16_tflops_sustained",
                          "peak_source": peaks["source"], "frac_of_burst_peak": kernel_tflops / peaks["tf_burst"],
-                         "executed_tensor_flop_per_point": 3 * 1_572_864 + 3 * 2 * 16 * 256 * 4 if engine == "tc_precise" else 1_572_864,
+                         "executed_tensor_flop_per_point": 3 * 1_572_864 if engine == "tc_precise" else 1_572_864,
                          "reverse_mode_equivalent_flop_per_point": 790_528},
-            "cpu_baseline": {"value": cpu_pps, "unit": "points/s", "cores": cores, "kind": "port",
-                             "sample": "262144 grid points, best of 2, oracle/siren_torch_port.field_query_with_grads (torch CPU)"},
+            "cpu_baseline": cpu_base,
             "isocontour": iso,
             "clocks": clocks,
             "torch": torch.__version__,
