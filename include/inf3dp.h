@@ -35,7 +35,9 @@ enum {
     INF3DP_MODE_AUTO = 0,       /* TC_PRECISE when the configuration supports it, else SIMT           */
     INF3DP_MODE_SIMT = 1,       /* FP32 CUDA-core kernel: any supported configuration, orders 0..2     */
     INF3DP_MODE_TC_PRECISE = 2, /* tcgen05 tensor cores, FP16 hi/lo split operands (3 MMAs), FP32 acc. */
-    INF3DP_MODE_TC_FAST = 3     /* tcgen05 tensor cores, single FP16 operands (does NOT meet 0.1 deg)  */
+    INF3DP_MODE_TC_FAST = 3,    /* tcgen05 tensor cores, single FP16 operands (does NOT meet 0.1 deg)  */
+    INF3DP_MODE_TC_REVERSE = 4  /* tcgen05 CTA pairs, reverse-mode value+gradient (out == 1, order == 1),
+                                   FP16 hi/lo split operands; needs the workspace of inf3dp_siren_jet_ws */
 };
 
 const char* inf3dp_last_error(void);
@@ -68,6 +70,16 @@ int inf3dp_siren_pack_weights(const float* const* weights_host, const float* con
  * out <= 4, order <= 1) and return INF3DP_EINVAL otherwise; AUTO falls back to SIMT for those. */
 int inf3dp_siren_jet(const void* packed, const float* x, int64_t n, int order, float* y, float* J, float* H,
                      int mode, inf3dp_stream_t stream);
+
+/* Same query with a caller-provided scratch buffer of inf3dp_siren_jet_workspace_bytes() bytes (device memory,
+ * contents irrelevant, must not be shared by launches that may run concurrently).  With a workspace, AUTO runs
+ * value+gradient queries of single-output sine networks on the reverse-mode engine (INF3DP_MODE_TC_REVERSE): the
+ * same forward + backward sweep the reference's autograd performs (diff_operators.py:128-132), fused in one kernel,
+ * half the tensor work of the forward-mode jet.  The scratch holds the cosines of two hidden layers per resident
+ * tile (256 KB per SM) between the sweeps. */
+size_t inf3dp_siren_jet_workspace_bytes(void);
+int inf3dp_siren_jet_ws(const void* packed, const float* x, int64_t n, int order, float* y, float* J, float* H,
+                        int mode, void* workspace, size_t workspace_bytes, inf3dp_stream_t stream);
 
 /* Unit normals: normals = grad / max(|grad|, eps), rows of 3 (torch.nn.functional.normalize as applied after
  * field_query_with_grads, toolpath_utils.py:180-181).  In-place (normals == grad) is allowed. */

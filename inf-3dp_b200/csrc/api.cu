@@ -186,6 +186,7 @@ int inf3dp_siren_pack_weights(const float* const* W, const float* const* b, int 
     h.off_wout = lay.off_wout; h.off_bout = lay.off_bout; h.off_tc = lay.tc_ok ? lay.off_tc : 0;
     h.total_bytes = lay.total;
     h.tc_scale = 1.f; h.tc_inv_scale = 1.f;
+    h.off_rev = lay.rev_ok ? lay.off_rev : 0; h.rev_ok = 0;
 
     pack_first_layer<<<(hidden + 255) / 256, 256, 0, st>>>(W[0], b[0], in_features, hidden, scale,
                                                           (float*)(base + lay.off_w0), (float*)(base + lay.off_b0));
@@ -203,6 +204,10 @@ int inf3dp_siren_pack_weights(const float* const* W, const float* const* b, int 
     if (lay.tc_ok) {
         int rc = siren_tc_pack(W, b, omega0, out_features, packed, lay, h, st);
         if (rc != INF3DP_OK) return rc;
+        if (lay.rev_ok) {
+            rc = siren_rev_pack(W, omega0, siren_tc_maxabs_bits(packed, lay), packed, lay, h, st);
+            if (rc != INF3DP_OK) return rc;
+        }
     }
     INF3DP_CUDA(cudaMemcpyAsync(packed, &h, sizeof(h), cudaMemcpyHostToDevice, st));
     // the header copy reads a stack object: make sure it has left the host before returning
@@ -212,8 +217,10 @@ int inf3dp_siren_pack_weights(const float* const* W, const float* const* b, int 
     return INF3DP_OK;
 }
 
-int inf3dp_siren_jet(const void* packed, const float* x, int64_t n, int order, float* y, float* J, float* H,
-                     int mode, inf3dp_stream_t stream) {
+size_t inf3dp_siren_jet_workspace_bytes(void) { return siren_rev_workspace_bytes(); }
+
+int inf3dp_siren_jet_ws(const void* packed, const float* x, int64_t n, int order, float* y, float* J, float* H,
+                        int mode, void* workspace, size_t workspace_bytes, inf3dp_stream_t stream) {
     INF3DP_CHECK_ARG(packed != nullptr, "siren_jet: null packed weights");
     INF3DP_CHECK_ARG(n >= 0, "siren_jet: negative point count");
     INF3DP_CHECK_ARG(order >= 0 && order <= 2, "siren_jet: order must be 0, 1 or 2 (got %d)", order);
@@ -227,8 +234,11 @@ int inf3dp_siren_jet(const void* packed, const float* x, int64_t n, int order, f
     INF3DP_CHECK_ARG(order == 0 || h.in_features == 3, "siren_jet: derivatives need in_features == 3");
     cudaStream_t st = (cudaStream_t)stream;
     const bool tc_capable = h.tc_ok && order <= 1;
+    const bool rev_capable = h.rev_ok && order == 1;
+    const bool have_ws = workspace != nullptr && workspace_bytes >= siren_rev_workspace_bytes();
     switch (mode) {
         case INF3DP_MODE_AUTO:
+            if (rev_capable && have_ws) return siren_rev_launch(packed, h, x, n, y, J, workspace, workspace_bytes, st);
             if (tc_capable) return siren_tc_launch(packed, h, x, n, order, y, J, true, st);
             return siren_simt_launch(packed, h, x, n, order, y, J, H, st);
         case INF3DP_MODE_SIMT:
@@ -238,10 +248,19 @@ int inf3dp_siren_jet(const void* packed, const float* x, int64_t n, int order, f
             INF3DP_CHECK_ARG(tc_capable, "siren_jet: tensor-core engine needs sine, in=3, hidden=256, 3 hidden layers, "
                              "out<=4 and order<=1");
             return siren_tc_launch(packed, h, x, n, order, y, J, mode == INF3DP_MODE_TC_PRECISE, st);
+        case INF3DP_MODE_TC_REVERSE:
+            INF3DP_CHECK_ARG(rev_capable, "siren_jet: reverse-mode engine needs sine, in=3, hidden=256, 3 hidden layers, "
+                             "out=1 and order=1");
+            return siren_rev_launch(packed, h, x, n, y, J, workspace, workspace_bytes, st);
         default:
             set_error("siren_jet: unknown mode %d", mode);
             return INF3DP_EINVAL;
     }
+}
+
+int inf3dp_siren_jet(const void* packed, const float* x, int64_t n, int order, float* y, float* J, float* H,
+                     int mode, inf3dp_stream_t stream) {
+    return inf3dp_siren_jet_ws(packed, x, n, order, y, J, H, mode, nullptr, 0, stream);
 }
 
 int inf3dp_unit_normals(const float* grad, int64_t n, float eps, float* normals, inf3dp_stream_t stream) {

@@ -76,16 +76,20 @@ struct SirenHeader {
     uint64_t total_bytes;
     float tc_scale;        // power-of-two pre-scale applied to the FP16 hidden weights (undone in the epilogue)
     float tc_inv_scale;
-    uint32_t pad[28];
+    uint64_t off_rev;      // reverse-mode tcgen05 operand images (see siren_rev.cu), 0 if !rev_ok
+    int rev_ok;            // flagship configuration with out_features == 1: the reverse-mode engine may be used
+    uint32_t pad[25];
 };
 static_assert(sizeof(SirenHeader) <= 256, "header must fit 256 bytes");
 
 struct SirenLayout {
-    size_t off_w0, off_b0, off_wt, off_b, off_wout, off_bout, off_tc, total;
-    bool tc_ok;
+    size_t off_w0, off_b0, off_wt, off_b, off_wout, off_bout, off_tc, off_rev, total;
+    bool tc_ok, rev_ok;
 };
 
-size_t siren_tc_section_bytes();  // siren_tc.cu
+size_t siren_tc_section_bytes();   // siren_tc.cu
+size_t siren_rev_section_bytes();  // siren_rev.cu
+size_t siren_rev_workspace_bytes();
 
 inline bool siren_config_supported(int in_features, int hidden, int L, int out) {
     return hidden == kHidden && (in_features == 3 || in_features == 4) && out >= 1 && out <= kMaxOut && L >= 0 &&
@@ -106,6 +110,10 @@ inline SirenLayout siren_layout(int in_features, int hidden, int L, int out, int
     l.off_tc = o;
     // the TC section is always reserved for in=3/L=3 so the blob size does not depend on the activation
     if (in_features == 3 && hidden == kHidden && L == 3 && out <= 8) o += siren_tc_section_bytes();
+    o = align_up(o, 1024);
+    l.rev_ok = l.tc_ok && out == 1;
+    l.off_rev = o;
+    if (in_features == 3 && hidden == kHidden && L == 3 && out == 1) o += siren_rev_section_bytes();
     l.total = align_up(o, 256);
     return l;
 }
@@ -117,5 +125,10 @@ int siren_tc_launch(const void* packed, const SirenHeader& h, const float* x, in
                     float* J, bool precise, cudaStream_t stream);
 int siren_tc_pack(const float* const* W, const float* const* b, float omega0, int out_features, void* packed,
                   const SirenLayout& lay, SirenHeader& hdr, cudaStream_t stream);
+const uint32_t* siren_tc_maxabs_bits(const void* packed, const SirenLayout& lay);  // device uint32[4], valid after siren_tc_pack
+int siren_rev_pack(const float* const* W, float omega0, const uint32_t* maxabs_bits, void* packed, const SirenLayout& lay,
+                   SirenHeader& hdr, cudaStream_t stream);
+int siren_rev_launch(const void* packed, const SirenHeader& h, const float* x, int64_t n, float* y, float* J, void* ws,
+                     size_t ws_bytes, cudaStream_t stream);
 
 }  // namespace inf3dp

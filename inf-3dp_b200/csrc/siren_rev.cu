@@ -1,0 +1,542 @@
+// tcgen05 REVERSE-mode engine of the fused SIREN value + gradient query (sm_100a), single-output networks
+// 3 -> 256 -> 256 -> 256 -> 256 -> 1 (sine): the SDF / slice / guidance fields of INF-3DP.
+//
+// Replaces modules.py:143-160 (forward) + diff_operators.py:128-132 (gradient via autograd) of the reference -- and it
+// evaluates exactly what the reference's autograd evaluates (one forward sweep, one backward sweep), but inside ONE
+// persistent kernel with every activation on chip:
+//
+//   forward   z_l = a_{l-1} W_l'^T + b_l'     a_l = sin z_l     c_l = cos z_l          l = 1..3   (W' = 30 W, b' = 30 b)
+//   output    y   = a_3 . w4 + b4             g_3 = w4 (.) c_3                                     (dy/dz_3)
+//   backward  g_{l-1} = (g_l W_l') (.) c_{l-1}                                            l = 3..1
+//   input     dy/dx_i = sum_f g_0[f] W_0'[f, i]
+//
+// A tile is 128 POINTS (row = point = one lane of tensor memory), so value + gradient cost 6 GEMMs of 128x256x256 per
+// 128 points -- half of the forward-mode jet (3 GEMMs per 32 points) -- and one sin + one cos per point-feature
+// instead of four MUFU evaluations.  Algorithmic work: 2 * (2*3*256 + 2*3*256^2 + 2*256) = 790 528 FLOP / point
+// (the "reverse-mode equivalent" figure).
+//
+// Execution (CTAS = 2, the shipped configuration): a CTA PAIR (cluster of 2, tcgen05 cta_group::2) owns 256 points.
+//   * Each GEMM is one M=256 x N=256 x K=16 UMMA per K-step and operand piece, issued by one thread of the leader CTA:
+//     A (activations or upstream gradients, FP16 hi + lo) is read from each CTA's TENSOR MEMORY, B (weights) from
+//     shared memory where each CTA holds only ITS 128 of the 256 B rows -- the L2 -> SM weight stream per SM is half
+//     of the single-CTA form, which is what the single-CTA forward engine is limited by -- and D accumulates in FP32 in
+//     the other 256 columns of tensor memory.  Three MMAs per K-step (a_hi W_hi + a_lo W_hi + a_hi W_lo): the measured
+//     accuracy need (scripts/emu_reverse.py: any unsplit operand, forward or backward, breaks the 0.1 degree bound).
+//   * 16 epilogue warps per CTA turn D into the next A operand IN PLACE (tcgen05.ld, FP32 math, FP16 hi/lo split,
+//     tcgen05.st over the same columns); the two halves of tensor memory swap roles after every GEMM.
+//   * cos z_1, cos z_2 are needed again by the backward sweep: they are stashed in FP32 (an FP16 stash fails parity) in a
+//     per-CTA scratch that stays in L2 (coalesced 512 B per warp store); cos z_3 is consumed immediately, cos z_0 is
+//     recomputed from the point in FP32.
+//   * Weight images stream L2 -> shared memory through a cp.async.bulk / mbarrier ring; the peer CTA forwards its
+//     "stage landed" to the leader with a remote mbarrier arrive; tcgen05.commit multicasts "stage free" and
+//     "accumulator ready" to both CTAs.
+// CTAS = 1 (developer configuration, INF3DP_REV_CTAS=1) runs the same schedule on one CTA with two N=128 MMAs.
+// Every mbarrier wait carries a watchdog that traps instead of hanging the GPU.
+#include <cuda_fp16.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace inf3dp {
+
+namespace {
+
+using namespace tcptx;
+
+// ---- packed REV section (offsets relative to SirenHeader::off_rev) ------------------------------------------------
+constexpr size_t kRevOffMisc = 0;           // float: G, 1/G
+constexpr size_t kRevOffW4 = 1024;          // float2[256]: (w4[f], G * w4[f])
+constexpr size_t kRevOffImg = 4096;         // 6 GEMMs x 2 N-halves x 16 K-steps x (hi 4 KB, lo 4 KB)
+constexpr size_t kPerKBytes = 8192;         // one K-step of one N-half: hi then lo, each 2 K-halves x 128 rows x 16 B
+constexpr size_t kHalfImgBytes = 16 * kPerKBytes;
+constexpr size_t kGemmImgBytes = 2 * kHalfImgBytes;
+constexpr size_t kRevSectionBytes = kRevOffImg + 6 * kGemmImgBytes;
+
+constexpr int kEpiWarps = 16;
+constexpr int kProducerWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;
+constexpr int kThreads = (kEpiWarps + 2) * 32;  // 576
+constexpr int kStageK = 4;                       // K-steps per ring stage
+constexpr size_t kStashBytesPerCta = 2 * 16 * 4 * 128 * 16;  // [2 layers][16 slices][4][128 rows] float4 = 256 KB
+
+template <int CTAS>
+struct RevCfg {
+    static constexpr int kStages = CTAS == 2 ? 4 : 3;
+    static constexpr uint32_t kStageBytes = (uint32_t)(kStageK * kPerKBytes) * (CTAS == 2 ? 1u : 2u);
+    static constexpr uint32_t kSmemRing = 0;
+    static constexpr uint32_t kSmemW0 = kStages * kStageBytes;   // float4[256] (wx, wy, wz, b0)
+    static constexpr uint32_t kSmemBias = kSmemW0 + 4096;        // float[3][256]
+    static constexpr uint32_t kSmemW4 = kSmemBias + 3072;        // float2[256]
+    static constexpr uint32_t kSmemPart = kSmemW4 + 2048;        // float[4 groups][4][128]
+    static constexpr uint32_t kSmemMisc = kSmemPart + 8192;      // inv_scale[3], b4, G, 1/G
+    static constexpr uint32_t kSmemBars = kSmemMisc + 64;
+    static constexpr int kBarWFull = 0, kBarWEmpty = kStages, kBarAReady = 2 * kStages, kBarDFull = 2 * kStages + 4,
+                         kNumBars = 2 * kStages + 5;
+    static constexpr uint32_t kSmemTmemPtr = kSmemBars + kNumBars * 8;
+    static constexpr uint32_t kSmemTotal = kSmemTmemPtr + 16;
+    static_assert(kSmemTotal <= 232448 - 1024, "shared memory budget");
+};
+
+template <int CTAS>
+__global__ void __launch_bounds__(kThreads, 1)
+siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __restrict__ x, int64_t n,
+                 float* __restrict__ y, float* __restrict__ J, float4* __restrict__ stash,
+                 unsigned long long* __restrict__ dbg) {
+    using C = RevCfg<CTAS>;
+    extern __shared__ unsigned char smem_dyn[];
+    const uint32_t sbase = (smem_u32(smem_dyn) + 1023u) & ~1023u;   // same offset in both CTAs of a pair
+    unsigned char* sptr = smem_dyn + (sbase - smem_u32(smem_dyn));
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = CTAS == 2 ? cluster_ctarank() : 0u;
+    const bool leader = rank == 0;
+    const char* tc = packed + h.off_tc;     // inverse scales live in the forward engine's section
+    const char* rv = packed + h.off_rev;
+
+    const int64_t num_tiles = (n + 127) / 128;
+    const int64_t num_units = (num_tiles + CTAS - 1) / CTAS;               // work unit = one tile per CTA of the pair
+    const int64_t unit0 = blockIdx.x / CTAS, unit_stride = gridDim.x / CTAS;
+    const int my_units = (int)((num_units - unit0 + unit_stride - 1) / unit_stride);
+
+    const uint32_t bars = sbase + C::kSmemBars;
+    auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
+
+    // ---- one-time setup --------------------------------------------------------------------------------------------
+    if (tid == 0) {
+        for (int s = 0; s < C::kStages; ++s) {
+            mbar_init(bar(C::kBarWFull + s), (CTAS == 2 && leader) ? 2 : 1);   // own producer (+ the peer's forward)
+            mbar_init(bar(C::kBarWEmpty + s), 1);
+        }
+        for (int r = 0; r < 4; ++r) mbar_init(bar(C::kBarAReady + r), kEpiWarps * CTAS);
+        mbar_init(bar(C::kBarDFull), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    {
+        float4* s_w0 = reinterpret_cast<float4*>(sptr + C::kSmemW0);
+        const float* g_w0 = reinterpret_cast<const float*>(packed + h.off_w0);
+        const float* g_b0 = reinterpret_cast<const float*>(packed + h.off_b0);
+        for (int i = tid; i < 256; i += kThreads) s_w0[i] = make_float4(g_w0[4 * i], g_w0[4 * i + 1], g_w0[4 * i + 2], g_b0[i]);
+        float* s_bias = reinterpret_cast<float*>(sptr + C::kSmemBias);
+        const float* g_bias = reinterpret_cast<const float*>(packed + h.off_b);   // f32 [3][256], omega folded
+        for (int i = tid; i < 3 * 256; i += kThreads) s_bias[i] = g_bias[i];
+        float2* s_w4 = reinterpret_cast<float2*>(sptr + C::kSmemW4);
+        const float2* g_w4 = reinterpret_cast<const float2*>(rv + kRevOffW4);
+        for (int i = tid; i < 256; i += kThreads) s_w4[i] = g_w4[i];
+        float* s_misc = reinterpret_cast<float*>(sptr + C::kSmemMisc);
+        if (tid < 3) s_misc[tid] = reinterpret_cast<const float*>(tc)[tid];                      // 1/S of layers 1..3
+        if (tid == 3) s_misc[3] = reinterpret_cast<const float*>(packed + h.off_bout)[0];          // b4
+        if (tid == 4) s_misc[4] = reinterpret_cast<const float*>(rv + kRevOffMisc)[1];             // 1/G
+    }
+    if (CTAS == 2) cluster_sync_all();   // both CTAs resident, barriers initialised, before any cross-CTA traffic
+    if (warp == kMmaWarp) {
+        if (CTAS == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                         ::"r"(sbase + C::kSmemTmemPtr), "r"(512) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                         ::"r"(sbase + C::kSmemTmemPtr), "r"(512) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sptr + C::kSmemTmemPtr);
+    const uint32_t regionP = tmem, regionQ = tmem + 256;
+
+    if (warp == kProducerWarp) {
+        // ================= weight producer (every CTA streams its own share of the B rows) =========================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int it = 0; it < my_units; ++it) {
+                for (int g = 0; g < 6; ++g) {
+                    const char* img = rv + kRevOffImg + (size_t)g * kGemmImgBytes;
+                    for (int r = 0; r < 4; ++r) {
+                        mbar_wait(bar(C::kBarWEmpty + stage), phase ^ 1u);
+                        const uint32_t dst = sbase + C::kSmemRing + stage * C::kStageBytes;
+                        const uint32_t bytes = (uint32_t)(kStageK * kPerKBytes);
+                        mbar_expect_tx(bar(C::kBarWFull + stage), C::kStageBytes);
+                        if (CTAS == 2) {
+                            bulk_g2s(dst, img + (size_t)rank * kHalfImgBytes + (size_t)r * bytes, bytes, bar(C::kBarWFull + stage));
+                        } else {
+                            bulk_g2s(dst, img + (size_t)r * bytes, bytes, bar(C::kBarWFull + stage));
+                            bulk_g2s(dst + bytes, img + kHalfImgBytes + (size_t)r * bytes, bytes, bar(C::kBarWFull + stage));
+                        }
+                        if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+                    }
+                }
+            }
+        }
+    } else if (warp == kMmaWarp) {
+        if (lane == 0 && leader) {
+            // ================= MMA issuer (leader CTA only) ===========================================================
+            constexpr uint32_t idesc = CTAS == 2 ? make_idesc_mn(256, 256) : make_idesc_mn(128, 128);
+            uint32_t stage = 0, wphase = 0, aphase = 0;
+            unsigned long long wait_a = 0, wait_w = 0;
+            const long long t_begin = clock64();
+            for (int it = 0; it < my_units; ++it) {
+                for (int g = 0; g < 6; ++g) {
+                    const uint32_t regA = (g & 1) ? regionQ : regionP;
+                    const uint32_t regD = (g & 1) ? regionP : regionQ;
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        long long t0 = dbg ? clock64() : 0;
+                        mbar_wait(bar(C::kBarAReady + r), aphase);
+                        long long t1 = dbg ? clock64() : 0;
+                        mbar_wait(bar(C::kBarWFull + stage), wphase);
+                        if (dbg) { wait_a += (unsigned long long)(t1 - t0); wait_w += (unsigned long long)(clock64() - t1); }
+                        tc_fence_after();
+                        const uint32_t ring = sbase + C::kSmemRing + stage * C::kStageBytes;
+#pragma unroll
+                        for (int tt = 0; tt < kStageK; ++tt) {
+                            const int t = kStageK * r + tt;
+                            const uint32_t a_hi = regA + 16u * (uint32_t)t;
+                            const uint32_t acc = t > 0 ? 1u : 0u;
+                            if (CTAS == 2) {
+                                const uint32_t sb = ring + (uint32_t)tt * (uint32_t)kPerKBytes;
+                                const uint64_t bh = make_desc(sb, 2048, 128), bl = make_desc(sb + 4096u, 2048, 128);
+                                mma_ts_pair(regD, a_hi, bh, idesc, acc);
+                                mma_ts_pair(regD, a_hi + 8u, bh, idesc, 1u);
+                                mma_ts_pair(regD, a_hi, bl, idesc, 1u);
+                            } else {
+#pragma unroll
+                                for (int hf = 0; hf < 2; ++hf) {
+                                    const uint32_t sb = ring + (uint32_t)hf * (uint32_t)(kStageK * kPerKBytes) +
+                                                        (uint32_t)tt * (uint32_t)kPerKBytes;
+                                    const uint64_t bh = make_desc(sb, 2048, 128), bl = make_desc(sb + 4096u, 2048, 128);
+                                    const uint32_t d = regD + 128u * (uint32_t)hf;
+                                    mma_ts(d, a_hi, bh, idesc, acc);
+                                    mma_ts(d, a_hi + 8u, bh, idesc, 1u);
+                                    mma_ts(d, a_hi, bl, idesc, 1u);
+                                }
+                            }
+                        }
+                        if (CTAS == 2) tc_commit_pair(bar(C::kBarWEmpty + stage), 3); else tc_commit(bar(C::kBarWEmpty + stage));
+                        if (++stage == C::kStages) { stage = 0; wphase ^= 1u; }
+                    }
+                    if (CTAS == 2) tc_commit_pair(bar(C::kBarDFull), 3); else tc_commit(bar(C::kBarDFull));
+                    aphase ^= 1u;
+                }
+            }
+            if (dbg && blockIdx.x == 0) {
+                dbg[0] = (unsigned long long)(clock64() - t_begin);
+                dbg[1] = wait_a;
+                dbg[2] = wait_w;
+                dbg[3] = (unsigned long long)my_units;
+            }
+        } else if (lane == 0 && CTAS == 2) {
+            // ================= peer CTA: forward "my half of the stage has landed" to the leader =====================
+            uint32_t stage = 0, phase = 0;
+            for (int it = 0; it < my_units; ++it) {
+                for (int gr = 0; gr < 24; ++gr) {
+                    mbar_wait(bar(C::kBarWFull + stage), phase);
+                    mbar_arrive_cluster(mapa_rank(bar(C::kBarWFull + stage), 0));
+                    if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else {
+        // ================= epilogue warps 0..15 ========================================================================
+        const int quad = warp & 3;           // TMEM lane quadrant this warp may access
+        const int grp = warp >> 2;           // slices grp, grp+4, grp+8, grp+12 (one MMA K-step each)
+        const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+        const int row = quad * 32 + lane;    // TMEM lane = point of the tile
+        const float4* s_w0 = reinterpret_cast<const float4*>(sptr + C::kSmemW0);
+        const float* s_bias = reinterpret_cast<const float*>(sptr + C::kSmemBias);
+        const float2* s_w4 = reinterpret_cast<const float2*>(sptr + C::kSmemW4);
+        const float* s_misc = reinterpret_cast<const float*>(sptr + C::kSmemMisc);
+        float* s_part = reinterpret_cast<float*>(sptr + C::kSmemPart);
+        float4* my_stash = stash + (size_t)blockIdx.x * (kStashBytesPerCta / 16) + row;
+        uint32_t a_ready_addr[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) a_ready_addr[r] = CTAS == 2 ? mapa_rank(bar(C::kBarAReady + r), 0) : bar(C::kBarAReady + r);
+        uint32_t dphase = 0;
+        unsigned long long wait_d = 0;
+        unsigned long long* pd = (dbg && lane == 0) ? &wait_d : nullptr;
+
+        auto publish = [&](int mi) {   // the slice just stored is visible to the MMA issuer
+            tc_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { if (CTAS == 2) mbar_arrive_cluster(a_ready_addr[mi]); else mbar_arrive(a_ready_addr[mi]); }
+        };
+
+        for (int it = 0; it < my_units; ++it) {
+            const int64_t tile = (unit0 + (int64_t)it * unit_stride) * CTAS + rank;
+            const int64_t pt = tile * 128 + row;
+            const bool pvalid = pt < n;
+            float px = 0.f, py = 0.f, pz = 0.f;
+            if (pvalid) { px = x[3 * pt]; py = x[3 * pt + 1]; pz = x[3 * pt + 2]; }
+
+            // ---- layer 0 (FP32): a0 = sin(W0' x + b0')  -> region P -------------------------------------------------
+#pragma unroll 1
+            for (int mi = 0; mi < 4; ++mi) {
+                const int m = grp + 4 * mi;
+                uint32_t o[16];
+#pragma unroll
+                for (int i = 0; i < 16; i += 2) {
+                    float r2[2];
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const float4 w = s_w0[16 * m + i + u];
+                        r2[u] = sin_layer0(fmaf(w.z, pz, fmaf(w.y, py, fmaf(w.x, px, w.w))));
+                    }
+                    split_pack<true>(r2[0], r2[1], o[i >> 1], o[8 + (i >> 1)]);
+                }
+                TC_ST16(regionP + lane_off + 16u * (uint32_t)m, o);
+                publish(mi);
+            }
+
+            float acc_y = 0.f, gx = 0.f, gy = 0.f, gz = 0.f;
+#pragma unroll
+            for (int g = 0; g < 6; ++g) {
+                const uint32_t regD = (g & 1) ? regionP : regionQ;
+                const float inv = s_misc[g < 3 ? g : 5 - g];              // 1/S of the layer this GEMM multiplies by
+                float4 cs[4];                                             // stashed cosines of the current slice
+                if (g == 3 || g == 4) {                                   // issue the first stash read under the wait
+                    const float4* sp = my_stash + (size_t)(((4 - g) * 16 + grp) * 4) * 128;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) cs[j] = __ldcg(sp + j * 128);
+                }
+                mbar_wait_warp(bar(C::kBarDFull), dphase, lane, pd);
+                dphase ^= 1u;
+                tc_fence_after();
+                uint32_t v[16];
+                TC_LD16(regD + lane_off + 16u * (uint32_t)grp, v);
+#pragma unroll 1
+                for (int mi = 0; mi < 4; ++mi) {
+                    const int m = grp + 4 * mi;
+                    const uint32_t addr = regD + lane_off + 16u * (uint32_t)m;
+                    tc_wait_ld();
+                    float cur[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) cur[i] = __uint_as_float(v[i]);
+                    if (mi < 3) TC_LD16(addr + 64u, v);   // prefetch the next slice (columns 16 (m + 4)) under the math
+                    uint32_t o[16];
+                    if (g < 3) {
+                        // forward: z = D / S + b'
+                        const float4* bp = reinterpret_cast<const float4*>(s_bias + g * 256 + 16 * m);
+                        float zz[16];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float4 b = bp[q];
+                            zz[4 * q] = fmaf(cur[4 * q], inv, b.x);
+                            zz[4 * q + 1] = fmaf(cur[4 * q + 1], inv, b.y);
+                            zz[4 * q + 2] = fmaf(cur[4 * q + 2], inv, b.z);
+                            zz[4 * q + 3] = fmaf(cur[4 * q + 3], inv, b.w);
+                        }
+                        if (g < 2) {
+                            float cc[16];
+#pragma unroll
+                            for (int i = 0; i < 16; i += 2) {
+                                const float s0 = sin_mufu(zz[i]), s1 = sin_mufu(zz[i + 1]);
+                                cc[i] = cos_mufu(zz[i]);
+                                cc[i + 1] = cos_mufu(zz[i + 1]);
+                                split_pack<true>(s0, s1, o[i >> 1], o[8 + (i >> 1)]);
+                            }
+                            float4* sp = my_stash + (size_t)((g * 16 + m) * 4) * 128;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                __stcg(sp + j * 128, make_float4(cc[4 * j], cc[4 * j + 1], cc[4 * j + 2], cc[4 * j + 3]));
+                        } else {
+                            // last hidden layer: y += w4 . sin z3 ; start the backward sweep with G w4 (.) cos z3
+#pragma unroll
+                            for (int i = 0; i < 16; i += 2) {
+                                const float2 w0 = s_w4[16 * m + i], w1 = s_w4[16 * m + i + 1];
+                                acc_y = fmaf(sin_mufu(zz[i]), w0.x, acc_y);
+                                acc_y = fmaf(sin_mufu(zz[i + 1]), w1.x, acc_y);
+                                split_pack<true>(cos_mufu(zz[i]) * w0.y, cos_mufu(zz[i + 1]) * w1.y, o[i >> 1], o[8 + (i >> 1)]);
+                            }
+                        }
+                    } else if (g < 5) {
+                        // backward through layer 6-g: g_{l-1} = (D / S) (.) cos z_{l-1}   (cosines from the stash)
+                        float gg[16];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            gg[4 * j] = cur[4 * j] * inv * cs[j].x;
+                            gg[4 * j + 1] = cur[4 * j + 1] * inv * cs[j].y;
+                            gg[4 * j + 2] = cur[4 * j + 2] * inv * cs[j].z;
+                            gg[4 * j + 3] = cur[4 * j + 3] * inv * cs[j].w;
+                        }
+                        if (mi < 3) {
+                            const float4* sp = my_stash + (size_t)(((4 - g) * 16 + m + 4) * 4) * 128;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) cs[j] = __ldcg(sp + j * 128);
+                        }
+#pragma unroll
+                        for (int i = 0; i < 16; i += 2) split_pack<true>(gg[i], gg[i + 1], o[i >> 1], o[8 + (i >> 1)]);
+                    } else {
+                        // input layer: g_0 = (D / S) (.) cos z_0 (recomputed), dy/dx += g_0 W0'
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const float4 w = s_w0[16 * m + i];
+                            const float z0 = fmaf(w.z, pz, fmaf(w.y, py, fmaf(w.x, px, w.w)));
+                            const float g0 = cur[i] * inv * cos_mufu(z0);
+                            gx = fmaf(g0, w.x, gx);
+                            gy = fmaf(g0, w.y, gy);
+                            gz = fmaf(g0, w.z, gz);
+                        }
+                    }
+                    if (g < 5) {
+                        TC_ST16(addr, o);
+                        publish(mi);
+                    }
+                }
+            }
+
+            // ---- outputs: sum the four feature-quarter partials of every point in a fixed order -------------------
+            s_part[(grp * 4 + 0) * 128 + row] = acc_y;
+            s_part[(grp * 4 + 1) * 128 + row] = gx;
+            s_part[(grp * 4 + 2) * 128 + row] = gy;
+            s_part[(grp * 4 + 3) * 128 + row] = gz;
+            asm volatile("bar.sync 1, 512;" ::: "memory");  // the 16 epilogue warps only
+            if (grp == 0 && pvalid) {
+                float r4[4];
+#pragma unroll
+                for (int o = 0; o < 4; ++o)
+                    r4[o] = ((s_part[(0 * 4 + o) * 128 + row] + s_part[(1 * 4 + o) * 128 + row]) +
+                             s_part[(2 * 4 + o) * 128 + row]) + s_part[(3 * 4 + o) * 128 + row];
+                const float inv_g = s_misc[4];
+                y[pt] = r4[0] + s_misc[3];
+                J[3 * pt] = r4[1] * inv_g;
+                J[3 * pt + 1] = r4[2] * inv_g;
+                J[3 * pt + 2] = r4[3] * inv_g;
+            }
+            // Hazards into the next unit: region P (next layer-0 target) holds the last D, which this warp has finished
+            // reading (tcgen05.wait::ld above); s_part is rewritten only after six more d_full phases, which need every
+            // epilogue warp (including the readers) to have published its next layer-0 slices.
+        }
+        if (dbg && blockIdx.x == 0 && lane == 0) dbg[8 + warp] = wait_d;
+    }
+
+    // ---- teardown ----------------------------------------------------------------------------------------------------
+    tc_fence_before();
+    __syncthreads();
+    if (CTAS == 2) cluster_sync_all();   // the peer's tensor memory is part of the leader's MMAs until both are done
+    if (warp == kMmaWarp) {
+        if (CTAS == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+    }
+}
+
+// ---- pack-time kernels ------------------------------------------------------------------------------------------------
+// power-of-two scale that puts max |w * mul| into [top/2, top)
+__device__ __forceinline__ float pow2_scale_to(float maxabs, int top_exp) {
+    if (!(maxabs > 0.f) || !isfinite(maxabs)) return 1.f;
+    int e;
+    frexpf(maxabs, &e);
+    return ldexpf(1.f, top_exp - e);
+}
+
+// One GEMM image: B[nb][kb] = S * omega0 * (transpose ? W[kb][nb] : W[nb][kb]), FP16 hi / lo, split in two N-halves,
+// each K-step stored as the K-major no-swizzle core-matrix image (8 rows x 16 B) the UMMA descriptor walks
+// (LBO = 2048 between the two K-halves, SBO = 128 between 8-row groups).
+__global__ void rev_pack_gemm_kernel(const float* __restrict__ W, float omega0, const uint32_t* __restrict__ maxabs_bits,
+                                     int transpose, char* __restrict__ img) {
+    const float scale = pow2_scale_to(omega0 * __uint_as_float(*maxabs_bits), 4);   // same S as the forward engine
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= 256 * 256) return;
+    const int nb = idx >> 8, kb = idx & 255;
+    const float w = transpose ? W[kb * 256 + nb] : W[nb * 256 + kb];
+    const float v = omega0 * w * scale;
+    const __half hi = __float2half_rn(v);
+    const __half lo = __float2half_rn(v - __half2float(hi));
+    const int half = nb >> 7, nl = nb & 127, t = kb >> 4, kc = (kb >> 3) & 1;
+    const size_t off = (size_t)half * kHalfImgBytes + (size_t)t * kPerKBytes + (size_t)kc * 2048 + (size_t)(nl >> 3) * 128 +
+                       (size_t)(nl & 7) * 16 + (size_t)(kb & 7) * 2;
+    *reinterpret_cast<__half*>(img + off) = hi;
+    *reinterpret_cast<__half*>(img + off + 4096) = lo;
+}
+
+__global__ void rev_pack_out_kernel(const float* __restrict__ W4, const uint32_t* __restrict__ maxabs_bits,
+                                    char* __restrict__ rv) {
+    const float G = pow2_scale_to(__uint_as_float(*maxabs_bits), 1);   // max |G w4| in [1, 2): 2^15 of FP16 headroom
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f == 0) {
+        float* misc = reinterpret_cast<float*>(rv + kRevOffMisc);
+        misc[0] = G;
+        misc[1] = 1.f / G;
+    }
+    if (f < 256) reinterpret_cast<float2*>(rv + kRevOffW4)[f] = make_float2(W4[f], G * W4[f]);
+}
+
+template <int CTAS>
+int launch_rev(const void* packed, const SirenHeader& h, const float* x, int64_t n, float* y, float* J, void* ws,
+               cudaStream_t stream) {
+    using C = RevCfg<CTAS>;
+    auto kern = siren_rev_kernel<CTAS>;
+    const int smem = (int)C::kSmemTotal + 1024;
+    INF3DP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int64_t tiles = (n + 127) / 128;
+    const int64_t units = (tiles + CTAS - 1) / CTAS;
+    const int64_t max_units = num_sms() / CTAS;
+    const int grid = (int)(units < max_units ? units : max_units) * CTAS;
+    static const bool debug = getenv("INF3DP_TC_DEBUG") != nullptr;
+    unsigned long long* dbg = nullptr;
+    if (debug) {
+        INF3DP_CUDA(cudaMalloc(&dbg, 64 * sizeof(unsigned long long)));
+        INF3DP_CUDA(cudaMemsetAsync(dbg, 0, 64 * sizeof(unsigned long long), stream));
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CTAS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    INF3DP_CUDA(cudaLaunchKernelEx(&cfg, kern, (const char*)packed, h, x, n, y, J, (float4*)ws, dbg));
+    INF3DP_LAUNCH_CHECK("siren_rev_kernel");
+    if (debug) {
+        unsigned long long hbuf[64];
+        INF3DP_CUDA(cudaMemcpyAsync(hbuf, dbg, sizeof(hbuf), cudaMemcpyDeviceToHost, stream));
+        INF3DP_CUDA(cudaStreamSynchronize(stream));
+        INF3DP_CUDA(cudaFree(dbg));
+        const double u = hbuf[3] ? (double)hbuf[3] : 1.0;
+        fprintf(stderr, "[inf3dp rev debug] CTAS=%d block0: %.0f units, %.0f cyc/unit (6 GEMMs); MMA thread blocked on a_ready %.0f, "
+                        "on w_full %.0f cyc/unit; epilogue warp0 blocked on d_full %.0f, warp5 %.0f, warp15 %.0f cyc/unit\n",
+                CTAS, u, hbuf[0] / u, hbuf[1] / u, hbuf[2] / u, hbuf[8] / u, hbuf[13] / u, hbuf[23] / u);
+    }
+    return INF3DP_OK;
+}
+
+}  // namespace
+
+size_t siren_rev_section_bytes() { return kRevSectionBytes; }
+
+size_t siren_rev_workspace_bytes() { return (size_t)num_sms() * kStashBytesPerCta; }
+
+// maxabs_bits: device uint32[4] = bit patterns of max |W| of layers 1..3 and of the output layer (filled by the forward
+// engine's pack step, which runs first on the same stream).
+int siren_rev_pack(const float* const* W, float omega0, const uint32_t* maxabs_bits, void* packed, const SirenLayout& lay,
+                   SirenHeader& hdr, cudaStream_t stream) {
+    char* rv = (char*)packed + lay.off_rev;
+    for (int g = 0; g < 6; ++g) {
+        const int layer = g < 3 ? 1 + g : 6 - g;   // forward: layers 1,2,3; backward: layers 3,2,1
+        rev_pack_gemm_kernel<<<256, 256, 0, stream>>>(W[layer], omega0, maxabs_bits + (layer - 1), g >= 3 ? 1 : 0,
+                                                      rv + kRevOffImg + (size_t)g * kGemmImgBytes);
+        INF3DP_LAUNCH_CHECK("rev_pack_gemm_kernel");
+    }
+    rev_pack_out_kernel<<<1, 256, 0, stream>>>(W[4], maxabs_bits + 3, rv);
+    INF3DP_LAUNCH_CHECK("rev_pack_out_kernel");
+    hdr.rev_ok = 1;
+    return INF3DP_OK;
+}
+
+int siren_rev_launch(const void* packed, const SirenHeader& h, const float* x, int64_t n, float* y, float* J, void* ws,
+                     size_t ws_bytes, cudaStream_t stream) {
+    INF3DP_CHECK_ARG(h.rev_ok && h.off_rev != 0, "siren_rev: packed weights carry no reverse-mode section");
+    INF3DP_CHECK_ARG(ws != nullptr && ws_bytes >= siren_rev_workspace_bytes(),
+                     "siren_rev: workspace of %zu bytes needed (inf3dp_siren_jet_workspace_bytes), got %zu",
+                     siren_rev_workspace_bytes(), ws_bytes);
+    static const int ctas = [] { const char* e = getenv("INF3DP_REV_CTAS"); return e && atoi(e) == 1 ? 1 : 2; }();
+    return ctas == 1 ? launch_rev<1>(packed, h, x, n, y, J, ws, stream) : launch_rev<2>(packed, h, x, n, y, J, ws, stream);
+}
+
+}  // namespace inf3dp

@@ -32,6 +32,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace inf3dp {
 
@@ -68,152 +69,8 @@ static_assert(kSmemTotal <= 232448 - 1024, "shared memory budget (1 KB reserved 
 constexpr int kEpiWarps = 16;
 constexpr int kProducerWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;
 constexpr int kThreadsTc = (kEpiWarps + 2) * 32;  // 576
-constexpr float kHalfPi = 1.57079632679489662f;
 
-// ---- PTX wrappers ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" ::"r"(bar), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    return ok != 0;
-}
-// Wait with a watchdog: a protocol bug traps (launch failure) instead of hanging the device.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
-    uint32_t spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if (++spins > 16u) __nanosleep(40);
-        if (spins > (1u << 24)) {  // >~ 1 s: a protocol bug, not a slow kernel
-            printf("inf3dp siren_tc: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x,
-                   threadIdx.x, bar, parity);
-            __trap();
-        }
-    }
-}
-// One lane polls, the warp follows (keeps 31 lanes' worth of spin instructions out of the issue slots).
-__device__ __forceinline__ void mbar_wait_timed(uint32_t bar, uint32_t parity, unsigned long long* acc);
-__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity, int lane, unsigned long long* acc = nullptr) {
-    if (lane == 0) mbar_wait_timed(bar, parity, acc);
-    __syncwarp();
-}
-// Developer instrumentation (INF3DP_TC_DEBUG=1): cycles spent blocked in a wait, accumulated per role.
-__device__ __forceinline__ void mbar_wait_timed(uint32_t bar, uint32_t parity, unsigned long long* acc) {
-    if (acc == nullptr) { mbar_wait(bar, parity); return; }
-    const long long t0 = clock64();
-    mbar_wait(bar, parity);
-    *acc += (unsigned long long)(clock64() - t0);
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// D[tmem] (+)= A[tmem] * B[smem descriptor]   (kind::f16, FP32 accumulate)
-__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
-    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}"
-                 ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
-}
-// K-major, no-swizzle UMMA shared-memory descriptor: core matrix = 8 rows x 16 bytes (128 contiguous bytes);
-// LBO = byte stride between the two K-halves of a K=16 step, SBO = byte stride between 8-row groups.
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-    d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
-    return d;                // base_offset 0, lbo_mode 0, layout_type SWIZZLE_NONE
-}
-// instruction descriptor: D=F32, A=B=F16, both K-major, M=128, N as given
-__host__ __device__ constexpr uint32_t make_idesc(int n) {
-    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-}
-
-#define TC_LD32(addr, v)                                                                                         \
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                       \
-                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,"  \
-                 "%26,%27,%28,%29,%30,%31}, [%32];"                                                              \
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),  \
-                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),       \
-                   "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),     \
-                   "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),     \
-                   "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                                                         \
-                 : "r"(addr) : "memory")
-
-#define TC_ST32(addr, v)                                                                                         \
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "                                                 \
-                 "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,"  \
-                 "%27,%28,%29,%30,%31,%32};"                                                                     \
-                 ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]),        \
-                   "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]),   \
-                   "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), \
-                   "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), \
-                   "r"(v[31]) : "memory")
-
-#define TC_ST16(addr, v)                                                                                         \
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "                                                 \
-                 "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"                                      \
-                 ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]),        \
-                   "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]),   \
-                   "r"(v[15]) : "memory")
-
-#define TC_ST8(addr, v)                                                                                          \
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"                         \
-                 ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]),        \
-                   "r"(v[7]) : "memory")
-
-#define TC_LD16(addr, v)                                                                                         \
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "                                                       \
-                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"                                \
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),  \
-                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),       \
-                   "=r"(v[15])                                                                                   \
-                 : "r"(addr) : "memory")
-
-__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
-__device__ __forceinline__ float sin_mufu(float x) {
-    float r;
-    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-// Layer 0 arguments reach |z| ~ 50 rad (30 * (|W0 x| + |b0|)).  sin.approx scales by 1/(2 pi) in FP32 (round toward
-// zero) and MUFU.SIN reduces modulo one revolution itself, so the absolute phase error is at most one FP32 ulp of
-// z / (2 pi) ~ 2^-20 revolutions = 6e-6 rad at |z| = 50 -- three orders of magnitude inside the 0.1 degree / 3.46e-4
-// parity budget (measured end to end in tests/test_gpu_siren.py), which is why no explicit Cody-Waite reduction
-// (4 more FP32 instructions per feature) is spent here.
-__device__ __forceinline__ float sin_layer0(float x) { return sin_mufu(x); }
-
-// Split two FP32 values into packed FP16 hi and lo words (value 0 in the low half = lower feature index).
-template <bool PRECISE>
-__device__ __forceinline__ void split_pack(float o0, float o1, uint32_t& hi, uint32_t& lo) {
-    const __half2 h = __floats2half2_rn(o0, o1);
-    hi = *reinterpret_cast<const uint32_t*>(&h);
-    if (PRECISE) {
-        const float2 hf = __half22float2(h);
-        const __half2 l = __floats2half2_rn(o0 - hf.x, o1 - hf.y);
-        lo = *reinterpret_cast<const uint32_t*>(&l);
-    } else {
-        lo = 0u;
-    }
-}
+using namespace tcptx;
 
 // ---------------------------------------------------------------------------------------------------------------
 template <int ORDER, bool PRECISE, int OUTC>
@@ -602,6 +459,10 @@ int launch_tc(const void* packed, const SirenHeader& h, const float* x, int64_t 
 }  // namespace
 
 size_t siren_tc_section_bytes() { return kTcSectionBytes; }
+
+const uint32_t* siren_tc_maxabs_bits(const void* packed, const SirenLayout& lay) {
+    return reinterpret_cast<const uint32_t*>((const char*)packed + lay.off_tc + kTcOffMaxAbs);
+}
 
 int siren_tc_pack(const float* const* W, const float* const* b, float omega0, int out_features, void* packed,
                   const SirenLayout& lay, SirenHeader& hdr, cudaStream_t stream) {

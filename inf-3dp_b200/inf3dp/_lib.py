@@ -13,8 +13,9 @@ LIB_PATH = os.path.join(_HERE, "libinf3dp.so")
 
 OK, EINVAL, ECUDA, EWORKSPACE, EOVERFLOW = 0, 1, 2, 3, 4
 ACT_SINE, ACT_RELU = 0, 1
-MODE_AUTO, MODE_SIMT, MODE_TC_PRECISE, MODE_TC_FAST = 0, 1, 2, 3
-MODES = {"auto": MODE_AUTO, "simt": MODE_SIMT, "tc_precise": MODE_TC_PRECISE, "tc_fast": MODE_TC_FAST}
+MODE_AUTO, MODE_SIMT, MODE_TC_PRECISE, MODE_TC_FAST, MODE_TC_REVERSE = 0, 1, 2, 3, 4
+MODES = {"auto": MODE_AUTO, "simt": MODE_SIMT, "tc_precise": MODE_TC_PRECISE, "tc_fast": MODE_TC_FAST,
+         "tc_reverse": MODE_TC_REVERSE}
 
 _vp, _i, _i64, _sz, _f = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_size_t, ctypes.c_float
 
@@ -25,6 +26,8 @@ SIGNATURES = {
     "inf3dp_siren_packed_bytes": (_sz, [_i, _i, _i, _i]),
     "inf3dp_siren_pack_weights": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _sz, _vp]),
     "inf3dp_siren_jet": (_i, [_vp, _vp, _i64, _i, _vp, _vp, _vp, _i, _vp]),
+    "inf3dp_siren_jet_workspace_bytes": (_sz, []),
+    "inf3dp_siren_jet_ws": (_i, [_vp, _vp, _i64, _i, _vp, _vp, _vp, _i, _vp, _sz, _vp]),
     "inf3dp_principal_curvatures": (_i, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "inf3dp_unit_normals": (_i, [_vp, _i64, _f, _vp, _vp]),
     "inf3dp_extract_isocontours_workspace_bytes": (_sz, [_i, _i, _i]),

@@ -28,7 +28,7 @@ _JET_MODE = {"mode": "auto"}
 
 
 def set_engine(mode: str):
-    """Select the execution engine for all SIREN queries: 'auto' | 'simt' | 'tc_precise' | 'tc_fast'."""
+    """Select the execution engine for all SIREN queries: 'auto' | 'simt' | 'tc_precise' | 'tc_fast' | 'tc_reverse'."""
     if mode not in _lib.MODES:
         raise ValueError(f"unknown engine {mode!r}; expected one of {sorted(_lib.MODES)}")
     _JET_MODE["mode"] = mode
@@ -76,6 +76,22 @@ class PackedWeights:
         return blob
 
 
+_WORKSPACES = {}
+
+
+def _jet_workspace(dev):
+    """Scratch of the reverse-mode engine, one per (device, stream): launches on one stream are ordered, launches
+    on different streams must not share it."""
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), torch.cuda.current_stream(dev).cuda_stream)
+    ws = _WORKSPACES.get(key)
+    if ws is None:
+        with torch.cuda.device(dev):
+            nbytes = _lib.lib().inf3dp_siren_jet_workspace_bytes()
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        _WORKSPACES[key] = ws
+    return ws
+
+
 def jet(blob, x, order, out_features, mode=None):
     """Raw fused query: x [n, in] (CUDA, f32) -> y [n,out], J [n,out,3] | None, H [n,out,3,3] | None."""
     if not x.is_cuda:
@@ -87,9 +103,11 @@ def jet(blob, x, order, out_features, mode=None):
     J = torch.empty((n, out_features, 3), dtype=torch.float32, device=dev) if order >= 1 else None
     H = torch.empty((n, out_features, 3, 3), dtype=torch.float32, device=dev) if order >= 2 else None
     m = _lib.MODES[mode or _JET_MODE["mode"]]
+    ws = _jet_workspace(dev) if (order == 1 and out_features == 1 and m in (_lib.MODE_AUTO, _lib.MODE_TC_REVERSE)) else None
     with torch.cuda.device(dev):
-        _lib.check(_lib.lib().inf3dp_siren_jet(_lib.ptr(blob), _lib.ptr(x), n, order, _lib.ptr(y), _lib.ptr(J),
-                                               _lib.ptr(H), m, _lib.stream_ptr(dev)))
+        _lib.check(_lib.lib().inf3dp_siren_jet_ws(_lib.ptr(blob), _lib.ptr(x), n, order, _lib.ptr(y), _lib.ptr(J),
+                                                  _lib.ptr(H), m, _lib.ptr(ws), ws.numel() if ws is not None else 0,
+                                                  _lib.stream_ptr(dev)))
     return y, J, H
 
 
