@@ -14,8 +14,10 @@ N*512^3-point job (weak scaling) and the step ends with one NCCL all-gather of t
 `value`  : whole-job points/s with coordinates resident in HBM (CUDA events, max over ranks).
 `e2e`    : the same metric through the public host-buffer API (inf3dp.HostPipeline): pinned host coordinates
            -> H2D -> fused kernel -> D2H of (value, gradient) into pinned host memory, copies inside the timed region.
-`roofline`: dominant kernel (siren_tc_kernel): algorithmic FLOPs (1 576 448 per point) / launch
-           duration against the measured dense tensor peak in MEASURED_PEAKS.json.
+`roofline`: dominant kernel (siren_rev_kernel, the reverse-mode tcgen05 engine): algorithmic FLOPs of the formulation it
+           executes (790 528 per point: one forward + one backward sweep, SURVEY.md 8d "reverse-mode equivalent")
+           / launch duration against the measured dense tensor peak in MEASURED_PEAKS.json.  INF3DP_ENGINE=tc_precise
+           selects the forward-mode jet engine instead (1 576 448 FLOP per point, the figure it is then judged on).
 `cpu_baseline`: the torch-CPU port of the reference's own path (oracle/siren_torch_port.py) on the host cores.
 `--impl reference`: that CPU path alone, same metric, bounded sample per step.
 Second metric (isocontour layers/s) is carried in the `isocontour` object of the same line.
@@ -33,7 +35,14 @@ for p in (ROOT, os.path.join(ROOT, "inf-3dp_b200")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
-FLOP_PER_POINT = 1_576_448          # forward-mode value+gradient, SURVEY.md section 8d
+FLOP_FORWARD_MODE = 1_576_448       # forward-mode value+gradient (value + 3 tangent columns), SURVEY.md section 8d
+FLOP_REVERSE_MODE = 790_528         # one forward + one backward sweep (what the reference's autograd executes), ibid.
+ENGINES = {  # engine -> (kernel, algorithmic FLOP/point, tensor FLOP/point actually issued, dtype note)
+    "tc_reverse": ("siren_rev_kernel<CTAS=2>", FLOP_REVERSE_MODE, 3 * 6 * 2 * 256 * 256, "f16x3-split operands, f32 accumulate"),
+    "tc_precise": ("siren_tc_kernel<ORDER=1,PRECISE,OUTC=1>", FLOP_FORWARD_MODE, 3 * 1_572_864, "f16x3-split operands, f32 accumulate"),
+    "tc_fast": ("siren_tc_kernel<ORDER=1,FAST,OUTC=1>", FLOP_FORWARD_MODE, 1_572_864, "f16 operands, f32 accumulate (NOT parity grade)"),
+    "simt": ("siren_simt_kernel<4>", FLOP_FORWARD_MODE, 0, "f32"),
+}
 GRID_N = 512
 WORKLOAD = "bunny SDF dense 512^3 grid evaluation (sdf_meshing path) with normals"
 
@@ -206,7 +215,8 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     peaks = load_peaks()
-    engine = os.environ.get("INF3DP_ENGINE", "tc_precise")  # the parity-passing engine is the headline
+    engine = os.environ.get("INF3DP_ENGINE", "tc_reverse")  # parity-grade reverse-mode engine is the headline
+    kernel_name, flop_per_point, issued_flop_per_point, dtype_note = ENGINES[engine]
 
     net = inf3dp.SingleBVPNet(type="sine", in_features=3)
     net.load_state_dict({f"net.net.{i}.0.{k}": torch.from_numpy(np.asarray(v)) for i, (W, b) in enumerate(golden_layers())
@@ -291,7 +301,7 @@ def run_ours(args):
     if rank == 0:
         total_pts = world * n
         value = total_pts / (ms_step / 1e3)
-        kernel_tflops = n * FLOP_PER_POINT / (ms_kernel / 1e3) / 1e12
+        kernel_tflops = n * flop_per_point / (ms_kernel / 1e3) / 1e12
         # the jet kernel runs ~0.5-1 s per launch under the power cap: the sustained cuBLAS figure is the fair peak
         peak = peaks["tf_sustained"]
         iso = bench_isocontours(dev, peaks)
@@ -304,7 +314,7 @@ def run_ours(args):
         line = {
             "metric": "siren_value_grad_points_per_s", "value": value, "unit": "points/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f16x3-split operands, f32 accumulate" if engine == "tc_precise" else engine,
+            "scaling": "weak", "vs_baseline": None, "dtype": dtype_note,
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "network": "3-256-256-256-256-1 sine, random init seed 2048",
                        "grid": GRID_N, "points_per_gpu": n, "engine": engine,
@@ -315,11 +325,15 @@ def run_ours(args):
                     "checksum": e2e_checksum},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": {"bound": "tensor", "achieved": kernel_tflops, "peak": peak, "unit": "TFLOP/s",
-                         "frac": kernel_tflops / peak, "traffic": None, "kernel": "siren_tc_kernel<ORDER=1,PRECISE,OUTC=1>" if engine == "tc_precise" else engine,
-                         "kernel_ms": ms_kernel, "flop_per_point": FLOP_PER_POINT, "peak_kind": "bf16_tflops_sustained",
+                         "frac": kernel_tflops / peak, "traffic": None, "kernel": kernel_name,
+                         "kernel_ms": ms_kernel, "flop_per_point": flop_per_point,
+                         "formulation": "reverse-mode (forward + backward sweep)" if engine == "tc_reverse" else "forward-mode jet",
+                         "peak_kind": "bf16_tflops_sustained",
                          "peak_source": peaks["source"], "frac_of_burst_peak": kernel_tflops / peaks["tf_burst"],
-                         "executed_tensor_flop_per_point": 3 * 1_572_864 if engine == "tc_precise" else 1_572_864,
-                         "reverse_mode_equivalent_flop_per_point": 790_528},
+                         "executed_tensor_flop_per_point": issued_flop_per_point,
+                         "tensor_pipe_frac_of_sustained_peak": n * issued_flop_per_point / (ms_kernel / 1e3) / 1e12 / peak,
+                         "forward_mode_flop_per_point": FLOP_FORWARD_MODE,
+                         "reverse_mode_flop_per_point": FLOP_REVERSE_MODE},
             "cpu_baseline": cpu_base,
             "isocontour": iso,
             "clocks": clocks,

@@ -186,7 +186,11 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
                         mbar_wait(bar(C::kBarAReady + r), aphase);
                         long long t1 = dbg ? clock64() : 0;
                         mbar_wait(bar(C::kBarWFull + stage), wphase);
-                        if (dbg) { wait_a += (unsigned long long)(t1 - t0); wait_w += (unsigned long long)(clock64() - t1); }
+                        if (dbg) {
+                            wait_a += (unsigned long long)(t1 - t0);
+                            wait_w += (unsigned long long)(clock64() - t1);
+                            if (blockIdx.x == 0) dbg[32 + g * 4 + r] += (unsigned long long)(t1 - t0);
+                        }
                         tc_fence_after();
                         const uint32_t ring = sbase + C::kSmemRing + stage * C::kStageBytes;
 #pragma unroll
@@ -499,6 +503,9 @@ int launch_rev(const void* packed, const SirenHeader& h, const float* x, int64_t
         INF3DP_CUDA(cudaStreamSynchronize(stream));
         INF3DP_CUDA(cudaFree(dbg));
         const double u = hbuf[3] ? (double)hbuf[3] : 1.0;
+        for (int g = 0; g < 6; ++g)
+            fprintf(stderr, "[inf3dp rev debug] GEMM %d: a_ready wait per round %.0f %.0f %.0f %.0f cyc\n", g, hbuf[32 + g * 4] / u,
+                    hbuf[33 + g * 4] / u, hbuf[34 + g * 4] / u, hbuf[35 + g * 4] / u);
         fprintf(stderr, "[inf3dp rev debug] CTAS=%d block0: %.0f units, %.0f cyc/unit (6 GEMMs); MMA thread blocked on a_ready %.0f, "
                         "on w_full %.0f cyc/unit; epilogue warp0 blocked on d_full %.0f, warp5 %.0f, warp15 %.0f cyc/unit\n",
                 CTAS, u, hbuf[0] / u, hbuf[1] / u, hbuf[2] / u, hbuf[8] / u, hbuf[13] / u, hbuf[23] / u);

@@ -24,9 +24,10 @@ def _net(golden, name="sdf", out=1):
 
 
 ENGINES = ["simt", "tc_precise"]
+ENGINES_GRAD1 = ENGINES + ["tc_reverse"]   # value+gradient of single-output networks: also the reverse-mode engine
 
 
-@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("engine", ENGINES_GRAD1)
 def test_value_gradient_vs_reference_golden(golden, engine):
     net = _net(golden)
     x = torch.from_numpy(golden["x"]).cuda()
@@ -119,8 +120,8 @@ def test_level_mlp_relu(golden):
     assert np.array_equal(lo.argmax(-1), golden["level/logits"].argmax(-1))
 
 
-@pytest.mark.parametrize("engine", ENGINES)
-@pytest.mark.parametrize("n", [0, 1, 31, 32, 33, 1000, 4097])
+@pytest.mark.parametrize("engine", ENGINES_GRAD1)
+@pytest.mark.parametrize("n", [0, 1, 31, 32, 33, 127, 129, 257, 1000, 4097, 37889])
 def test_ragged_sizes_and_batch_split_invariance(golden, engine, n):
     net = _net(golden)
     g = torch.Generator().manual_seed(n)
@@ -138,7 +139,7 @@ def test_ragged_sizes_and_batch_split_invariance(golden, engine, n):
         assert torch.equal(y2, y[k:]) and torch.equal(J2, J[k:])
 
 
-@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("engine", ENGINES_GRAD1)
 def test_million_points_size_independent_properties(golden, engine):
     """Full-size property check (no oracle at this size): determinism, batch-split invariance, and agreement
     between engines on a sample checked against the oracle."""
@@ -164,3 +165,62 @@ def test_weights_repack_after_update(golden):
         net.net.net[4][0].bias.add_(1.0)
     y1, _, _ = net.query(x, order=0, mode="simt")
     assert torch.allclose(y1, y0 + 1.0, atol=1e-6)
+
+
+def test_reverse_engine_is_the_default_and_needs_its_workspace(golden):
+    """AUTO routes value+gradient of single-output sine networks to the reverse-mode engine (bit-identical results),
+    and the C ABI refuses that engine without the scratch buffer instead of silently running something else."""
+    import ctypes
+    import inf3dp
+    from inf3dp import _lib
+    net = _net(golden)
+    x = torch.from_numpy(golden["x"]).cuda()
+    ya, Ja, _ = net.query(x, order=1, mode="auto")
+    yr, Jr, _ = net.query(x, order=1, mode="tc_reverse")
+    assert torch.equal(ya, yr) and torch.equal(Ja, Jr)
+    ws, bs = net._weights()
+    blob = net._packed.get(ws, bs)
+    y = torch.empty((len(x), 1), device="cuda"); J = torch.empty((len(x), 1, 3), device="cuda")
+    L = _lib.lib()
+    rc = L.inf3dp_siren_jet_ws(_lib.ptr(blob), _lib.ptr(x), len(x), 1, _lib.ptr(y), _lib.ptr(J), None,
+                               _lib.MODE_TC_REVERSE, None, 0, _lib.stream_ptr(x.device))
+    assert rc == _lib.EINVAL and b"workspace" in L.inf3dp_last_error()
+    small = torch.empty(1024, dtype=torch.uint8, device="cuda")
+    rc = L.inf3dp_siren_jet_ws(_lib.ptr(blob), _lib.ptr(x), len(x), 1, _lib.ptr(y), _lib.ptr(J), None,
+                               _lib.MODE_TC_REVERSE, _lib.ptr(small), 1024, _lib.stream_ptr(x.device))
+    assert rc == _lib.EINVAL
+    # four-output networks are not served by the reverse engine
+    q = _net(golden, "quat", 4)
+    with pytest.raises(RuntimeError):
+        q.query(x, order=1, mode="tc_reverse")
+
+
+def test_reverse_engine_other_field_networks(golden):
+    """A second and third weight set (different seeds: the slice / guidance field role) through the reverse engine."""
+    import inf3dp
+    for seed in (7, 99):
+        torch.manual_seed(seed)
+        net = inf3dp.SingleBVPNet(type="sine", in_features=3).cuda()
+        layers = so.params_from_state_dict({k: v.detach().cpu().numpy() for k, v in net.state_dict().items()})
+        g = torch.Generator().manual_seed(seed)
+        x = (torch.rand(20000, 3, generator=g) * 2 - 1).cuda()
+        y, J, _ = net.query(x, order=1, mode="tc_reverse")
+        yo, Jo, _ = so.siren_jet(layers, x.cpu().numpy().astype(np.float64), order=1)
+        assert np.abs(y.cpu().numpy() - yo).max() <= TOL_F
+        assert so.angle_deg(J.cpu().numpy()[:, 0], Jo[:, 0]).max() <= TOL_ANGLE
+        # gradient magnitude too (the angle alone would not see a wrong scale)
+        rel = np.abs(np.linalg.norm(J.cpu().numpy()[:, 0], axis=1) / np.linalg.norm(Jo[:, 0], axis=1) - 1.0)
+        assert rel.max() <= 2e-3
+
+
+@pytest.mark.parametrize("engine", ENGINES_GRAD1)
+def test_slice_field_vs_reference_golden(golden, engine):
+    """The slice / guidance field network of the golden file (second weight set recorded from the reference)."""
+    import inf3dp
+    torch.manual_seed(2048)  # exp_scripts/train_sdf.py:13; construction order of tests/golden/make_golden.py: sdf, slice, ...
+    inf3dp.SingleBVPNet(type="sine", in_features=3)
+    net = inf3dp.SingleBVPNet(type="sine", in_features=3).cuda()   # the slice network (weights pinned by sha in test_dropin)
+    x = torch.from_numpy(golden["x"]).cuda()
+    y, J, _ = net.query(x, order=1, mode=engine)
+    assert np.abs(y.cpu().numpy() - golden["slice/y"]).max() <= TOL_F
+    assert so.angle_deg(J.cpu().numpy()[:, 0], golden["slice/grad"]).max() <= TOL_ANGLE
