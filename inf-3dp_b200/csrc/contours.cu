@@ -24,6 +24,8 @@
 #include <mutex>
 #include <stdlib.h>
 
+#include <vector>
+
 #include "common.cuh"
 
 namespace inf3dp {
@@ -73,7 +75,7 @@ inline int pow2_at_least(long long v) {
 ContourWs carve(void* base, int K, int cap) {
     ContourWs w{};
     w.cap = cap;
-    w.hcap = pow2_at_least(4ll * w.cap);
+    w.hcap = pow2_at_least(2ll * w.cap);
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
     char* b = (char*)base;
@@ -139,6 +141,33 @@ __device__ __forceinline__ bool face_segment(const FaceData& fd, float iso, cons
     return true;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// The segment pool is written by `emit`, then read by `link` and `walk` WHILE the zero fill streams 12 K F bytes
+// through the L2.  Pool accesses carry an L2 evict_last policy (the fill's stores are evict-first, __stcs), so the
+// pool stays cache resident and the latency-bound chain does not queue behind the fill in DRAM.
+__device__ __forceinline__ unsigned long long keep_policy() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ int ld_keep(const int* a, unsigned long long pol) {
+    int v;
+    asm volatile("ld.global.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(v) : "l"(a), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ float ld_keep(const float* a, unsigned long long pol) {
+    float v;
+    asm volatile("ld.global.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(a), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void st_keep(int* a, int v, unsigned long long pol) {
+    asm volatile("st.global.L2::cache_hint.b32 [%0], %1, %2;" ::"l"(a), "r"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_keep(float* a, float v, unsigned long long pol) {
+    asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(a), "f"(v), "l"(pol) : "memory");
+}
+
 __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
     x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
     return x;
@@ -185,6 +214,7 @@ contour_faces_kernel(const float* __restrict__ V, const int* __restrict__ F, con
 
     const int lane = threadIdx.x & 31;
     const int hmask = EMIT ? (w.hdr[2] - 1) : 0;
+    const unsigned long long keep = keep_policy();
     const int face_base = blockIdx.x * blockDim.x;
     // every warp runs whole: inactive lanes carry an empty isovalue window
     const int t = face_base + threadIdx.x;
@@ -225,10 +255,10 @@ contour_faces_kernel(const float* __restrict__ V, const int* __restrict__ F, con
             if (lane == leader) basei = atomicAdd(&w.cursor[k], __popc(peers));
             basei = __shfl_sync(peers, basei, leader);
             const int slot = w.seg_offset[k] + basei + rank;
-            w.seg_face[slot] = t;
+            st_keep(&w.seg_face[slot], t, keep);
             float* sp = w.seg_pts + 6ll * slot;
 #pragma unroll
-            for (int d = 0; d < 6; ++d) sp[d] = p[d];
+            for (int d = 0; d < 6; ++d) st_keep(sp + d, p[d], keep);
             w.used[slot] = 0;
             // register both endpoints under their (isovalue, mesh edge) key
 #pragma unroll
@@ -248,7 +278,7 @@ contour_faces_kernel(const float* __restrict__ V, const int* __restrict__ F, con
                     }
                     hs = (hs + 1) & hmask;
                 }
-                w.seg_slot[id] = hs;
+                st_keep(&w.seg_slot[id], hs, keep);
             }
         }
     }
@@ -279,7 +309,7 @@ __global__ void contour_scan_kernel(int K, ContourWs w) {
         w.hdr[1] = total;
         w.hdr[3] = w.cap;
         w.hdr[0] = total > w.cap ? 1 : 0;
-        long long want = 4ll * total;
+        long long want = 2ll * total;   // one key per crossed mesh edge (~ total): load factor 0.25 .. 0.5
         long long p = 1024;
         while (p < want) p <<= 1;
         if (p > w.hcap) p = w.hcap;
@@ -300,19 +330,21 @@ __global__ void contour_hash_clear_kernel(ContourWs w) {
 __global__ void contour_link_kernel(ContourWs w) {
     if (w.hdr[0] != 0) return;
     const int n = 2 * w.hdr[1];
+    const unsigned long long keep = keep_policy();
     for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < n; id += gridDim.x * blockDim.x) {
-        const int hs = w.seg_slot[id];
+        const int hs = ld_keep(&w.seg_slot[id], keep);
         const int a = w.hvals[2 * hs], b = w.hvals[2 * hs + 1];
         int partner = (a == id) ? b : (b == id ? a : -1);
         if (partner >= 0) {
             const float* p = w.seg_pts + 3ll * id;  // [seg][side][3] == flat [id][3]
             const float* q = w.seg_pts + 3ll * partner;
-            const float dx = p[0] - q[0], dy = p[1] - q[1], dz = p[2] - q[2];
+            const float dx = ld_keep(p, keep) - ld_keep(q, keep), dy = ld_keep(p + 1, keep) - ld_keep(q + 1, keep),
+                        dz = ld_keep(p + 2, keep) - ld_keep(q + 2, keep);
             const float d = dx * dx + dy * dy + dz * dz;
             const float thr = 1e-6 * 1e-6;  // isocontours.cu:111
             if (!(d < thr)) partner = -1;
         }
-        w.seg_link[id] = partner;
+        st_keep(&w.seg_link[id], partner, keep);
     }
 }
 
@@ -323,57 +355,85 @@ __global__ void contour_link_kernel(ContourWs w) {
 // seeding kills the one link that leads into the seed's p1 (link[partner(seed.p1)] = -1).  A closed loop coming
 // back to its seed, or a later walk reaching an earlier seed from behind, then reads -1 and stops: exactly the
 // reference's "no unused segment within the merge radius" exit (isocontours.cu:157-203).
-constexpr int kWalkThreads = 256;
-constexpr int kWalkSmemSegs = 6144;  // segments per isovalue walked entirely in shared memory (links + order + used)
-constexpr int kWalkSmemBytes = kWalkSmemSegs * (8 + 8 + 4);
+constexpr int kWalkThreads = 512;
+// Segments per isovalue handled entirely in shared memory (20 bytes per segment: 100 KB, two walk CTAs per SM, so
+// K <= 296 isovalues are one wave).  Larger isovalues walk in the workspace.
+constexpr int kWalkSmemSegs = 5120;
+constexpr int kWalkSmemBytes = kWalkSmemSegs * 20;
+constexpr int kRankPerThread = 2 * kWalkSmemSegs / kWalkThreads;   // traversal states per thread in the ranked path (24)
+constexpr int kRankMaxLoops = 320;   // contour pieces (closed loops + pieces of open chains) per isovalue
+constexpr int kRankMaxPaths = 32;    // open chains per isovalue
 
-__global__ void __launch_bounds__(kWalkThreads)
-contour_walk_kernel(int nF, ContourWs w, float* __restrict__ merged, int* __restrict__ nums) {
-    extern __shared__ int s_dyn[];
-    const int k = blockIdx.x;
+template <typename IdxT> struct WalkIdx;
+template <> struct WalkIdx<int> {
+    static constexpr int kNone = -1, kSep = -2;
+    __device__ static bool none(int v) { return v < 0; }
+    __device__ static bool is_point(int v) { return v >= 0; }
+};
+template <> struct WalkIdx<unsigned short> {
+    static constexpr unsigned short kNone = 0xFFFFu, kSep = 0xFFFEu;
+    __device__ static bool none(unsigned short v) { return v == kNone; }
+    __device__ static bool is_point(unsigned short v) { return v < kSep; }
+};
+
+// Serial walk (isovalues with open chains, or too large for shared memory).  nx[e] = entry endpoint of the segment
+// that follows the segment entered through endpoint e (link[e ^ 1]), so the chain is ONE dependent load per step;
+// face[] is a private copy of the face ids so that the seed searches stay out of global memory when the working set
+// is in shared memory (the zero fill saturates HBM while this runs).
+template <typename IdxT, typename UsedT>
+__device__ __forceinline__ void walk_isovalue(int S, int off, int nF, int k, const ContourWs& w, IdxT* nx, IdxT* order,
+                                              UsedT* used, int* face_copy, const unsigned short* by_face,
+                                              float* __restrict__ merged, int* __restrict__ nums) {
+    using X = WalkIdx<IdxT>;
     __shared__ int s_face[kWalkThreads / 32];
     __shared__ int s_best[kWalkThreads / 32];
     __shared__ int s_seed;
-    const bool overflow = w.hdr[0] != 0;
-    const int S = overflow ? 0 : w.seg_count[k];
-    const int off = w.seg_offset[k];
-    if (S == 0) {
-        if (threadIdx.x == 0) { nums[k] = 0; w.rows_used[k] = 0; }
-        return;
+    __shared__ int s_rows;
+    const unsigned long long keep = keep_policy();
+    for (int i = threadIdx.x; i < S; i += blockDim.x) {
+        const int a = ld_keep(&w.seg_link[2ll * off + 2 * i], keep), b = ld_keep(&w.seg_link[2ll * off + 2 * i + 1], keep);
+        nx[2 * i] = b < 0 ? X::kNone : (IdxT)(b - 2 * off);       // all partners belong to the same isovalue
+        nx[2 * i + 1] = a < 0 ? X::kNone : (IdxT)(a - 2 * off);
+        used[i] = 0;
+        if (face_copy) face_copy[i] = ld_keep(&w.seg_face[off + i], keep);
     }
-    // Working set of the chain walk: partner links (local endpoint ids), the row order being recorded and the
-    // per-segment consumed flags.  In shared memory when the isovalue fits (no global traffic on the chain, which
-    // matters because the zero fill saturates HBM concurrently), in the workspace otherwise.
-    int* lk;
-    int* order;
-    int* used;
-    const bool in_smem = S <= kWalkSmemSegs;
-    if (in_smem) {
-        lk = s_dyn;
-        order = s_dyn + 2 * kWalkSmemSegs;
-        used = s_dyn + 4 * kWalkSmemSegs;
-    } else {
-        lk = w.seg_link + 2ll * off;
-        order = w.seg_order + 2ll * off;
-        used = w.seg_slot + 2ll * off;  // the hash-slot array is dead after `link`: reuse it as int flags
-    }
-    for (int i = threadIdx.x; i < 2 * S; i += blockDim.x) {
-        const int g = w.seg_link[2ll * off + i];
-        lk[i] = g < 0 ? -1 : g - 2 * off;  // all partners belong to the same isovalue
-    }
-    for (int i = threadIdx.x; i < S; i += blockDim.x) used[i] = 0;
+    const int* face = face_copy ? face_copy : w.seg_face + off;
     const float* pts = w.seg_pts + 6ll * off;       // [S][2][3] == flat [endpoint][3]; rows <= S + C <= 2S
     float* out = merged + (size_t)k * nF * 3;
-    __shared__ int s_rows;
     int row = 0, contours = 0;
     __syncthreads();
+    if (by_face != nullptr) {
+        // Seeds in ascending face order = one pass over the segments sorted by face id (sorted once, in parallel,
+        // by the caller): the whole walk is a single thread touching shared memory only, no block-wide
+        // synchronisation per contour piece.
+        if (threadIdx.x == 0) {
+            for (int c = 0; c < S; ++c) {
+                const int seed = by_face[c];
+                if (used[seed]) continue;
+                if (contours > 0) order[row++] = X::kSep;  // separator between loops (isocontours.cu:135-140)
+                order[row++] = (IdxT)(2 * seed);           // seed.p1 (isocontours.cu:143-146)
+                used[seed] = 1;
+                ++contours;
+                const IdxT z = nx[2 * seed + 1];           // partner of seed.p1: the link into the seed dies
+                if (!X::none(z)) nx[(int)z ^ 1] = X::kNone;
+                int e = 2 * seed;                          // entered through p1, tail = p2 (isocontours.cu:151-153)
+                while (true) {
+                    const IdxT y = nx[e];                  // the only dependent load of the chain
+                    if (X::none(y)) break;
+                    e = (int)y;
+                    order[row++] = (IdxT)(e ^ 1);          // left through its other endpoint: the emitted row
+                    used[e >> 1] = 1;
+                }
+            }
+        }
+    } else {
     // phase 1: one thread records the row order (endpoint ids); nothing but shared-memory loads on its chain
     while (true) {
         // lowest face id among unused segments (ascending-face seed order); face ids are unique per isovalue
         int best_face = 0x7fffffff, best_seg = -1;
         for (int i = threadIdx.x; i < S; i += blockDim.x) {
             if (!used[i]) {
-                const int f = w.seg_face[off + i];
+                const int f = face[i];
                 if (f < best_face) { best_face = f; best_seg = i; }
             }
         }
@@ -393,26 +453,28 @@ contour_walk_kernel(int nF, ContourWs w, float* __restrict__ merged, int* __rest
         const int seed = s_seed;
         if (seed < 0) break;
         if (threadIdx.x == 0) {
-            if (contours > 0) order[row++] = -2;      // separator between loops (isocontours.cu:135-140)
-            order[row++] = 2 * seed;                   // seed.p1 (isocontours.cu:143-146)
+            if (contours > 0) order[row++] = X::kSep;  // separator between loops (isocontours.cu:135-140)
+            order[row++] = (IdxT)(2 * seed);           // seed.p1 (isocontours.cu:143-146)
             used[seed] = 1;
             ++contours;
-            // links into the seed become dead ends: the loop closes when the walk comes back to it
-            const int z = lk[2 * seed];
-            if (z >= 0) lk[z] = -1;
-            int cur_end = 2 * seed + 1;                // tail = seed.p2 (isocontours.cu:151-153)
+            // the link into the seed's p1 becomes a dead end: the loop closes when the walk comes back to it, and a
+            // later walk that reaches this seed from behind stops there
+            const IdxT z = nx[2 * seed + 1];           // partner of seed.p1
+            if (!X::none(z)) nx[(int)z ^ 1] = X::kNone;
+            int e = 2 * seed;                          // entered through p1, tail = p2 (isocontours.cu:151-153)
             while (true) {
-                const int y = lk[cur_end];             // entry endpoint of the next segment (the only dependent load)
-                if (y < 0) break;
-                cur_end = y ^ 1;                       // leave through its other endpoint ...
-                order[row++] = cur_end;                // ... whose point is the emitted row
-                used[y >> 1] = 1;
+                const IdxT y = nx[e];                  // entry endpoint of the next segment (the only dependent load)
+                if (X::none(y)) break;
+                e = (int)y;
+                order[row++] = (IdxT)(e ^ 1);          // it is left through its other endpoint: the emitted row
+                used[e >> 1] = 1;
             }
         }
         __syncthreads();  // `used` written by thread 0 is visible to the next seed search
     }
+    }
     if (threadIdx.x == 0) {
-        if (contours > 0) order[row++] = -2;           // trailing separator (isocontours.cu:205-210)
+        if (contours > 0) order[row++] = X::kSep;      // trailing separator (isocontours.cu:205-210)
         nums[k] = contours;
         s_rows = row;
         w.rows_used[k] = min(row, nF);
@@ -421,10 +483,358 @@ contour_walk_kernel(int nF, ContourWs w, float* __restrict__ merged, int* __rest
     // phase 2: all threads gather the points and write the row stream
     const int rows = min(s_rows, nF);
     for (int r = threadIdx.x; r < rows; r += blockDim.x) {
-        const int e = order[r];
+        const IdxT e = order[r];
         float a = -1e9f, b = -1e9f, c = -1e9f;
-        if (e >= 0) { const float* q = pts + 3ll * e; a = q[0]; b = q[1]; c = q[2]; }
+        if (X::is_point(e)) { const float* q = pts + 3ll * (int)e; a = ld_keep(q, keep); b = ld_keep(q + 1, keep); c = ld_keep(q + 2, keep); }
         out[3ll * r] = a; out[3ll * r + 1] = b; out[3ll * r + 2] = c;
+    }
+}
+
+// Parallel walk of one isovalue.  The serial walk of the reference is a traversal of the functional graph
+//   next(e) = link[e ^ 1]        on "states" e = endpoint through which a segment is entered,
+// so its result can be computed with pointer doubling instead of one dependent load per segment:
+//
+// CLOSED loops (every endpoint has its partner -- watertight meshes).  Every undirected loop is two directed cycles of
+// states; the reference starts at the loop's lowest face (ascending-face seed order) and enters that segment through
+// p1, i.e. it follows the cycle that contains the EVEN state of the lowest-face segment.  One doubling pass carries,
+// per state, (minimum over the next 2^t states of key = 2 * face + parity(state), distance to that minimum): after
+// ceil(log2 S) rounds every state knows its loop's seed face, whether its cycle is the walked direction (key even) and
+// how far behind the seed it is.
+//
+// OPEN chains (a partner is missing: mesh boundary, or a pair outside the reference's merge radius).  A first doubling
+// pass gives every state its distance to the dead end of its directed path and the identity of that dead end; each
+// chain is then laid out by position and the reference's seed order is replayed on INTERVALS: the lowest unused face
+// of the chain seeds a piece that runs from there to the end of the remaining interval in the direction of the seed's
+// p1 -> p2 traversal (the walk only stops at a dead end or at the back of an earlier seed, isocontours.cu:157-203), the
+// rest of the interval is seeded again.  One block-wide arg-min per piece instead of one dependent load per segment.
+//
+// Pieces of both kinds are ordered by seed face, row offsets are a prefix sum of (length + 1), and every state of a walked
+// direction writes its own output row: rank 0 -> the seed's p1, rank r >= 1 -> the exit endpoint of the r-th segment
+// (isocontours.cu:143-203), then the (-1e9) separator row (:135-140, :205-210).
+// Returns false (nothing written) when a list capacity is exceeded: the caller then walks the isovalue serially.
+__device__ bool walk_ranked(int S, int off, int nF, int k, const ContourWs& w, unsigned char* smem,
+                            float* __restrict__ merged, int* __restrict__ nums) {
+    unsigned short* J = reinterpret_cast<unsigned short*>(smem);                 // [2S] jump pointers
+    unsigned short* D = J + 2 * kWalkSmemSegs;                                   // [2S] distances
+    int* V = reinterpret_cast<int*>(D + 2 * kWalkSmemSegs);                      // [2S] keys (closed) / dead-end info (open)
+    unsigned short* NX = reinterpret_cast<unsigned short*>(V + 2 * kWalkSmemSegs);  // [2S] next(e); later P | Q
+    unsigned short* P = NX;                                                      // [S] state at a chain position
+    unsigned short* Q = NX + kWalkSmemSegs;                                      // [S] piece of a chain position
+    constexpr unsigned short kNone = 0xFFFFu;
+    __shared__ int s_nloops, s_npaths, s_slot;
+    __shared__ int s_lface[kRankMaxLoops], s_llen[kRankMaxLoops];   // piece: seed face, length (discovery order)
+    __shared__ int s_linfo[kRankMaxLoops];                          // open piece: seed position << 1 | reverse flag
+    __shared__ int s_lbase[kRankMaxLoops];                          // piece: first output row
+    __shared__ int s_sface[kRankMaxLoops], s_slen[kRankMaxLoops], s_sbase[kRankMaxLoops];   // sorted by seed face
+    __shared__ int s_pterm[kRankMaxPaths], s_plen[kRankMaxPaths], s_pbase[kRankMaxPaths];   // chain: dead end, length, P offset
+    __shared__ unsigned long long s_cmin[kWalkSmemSegs / 32];   // per 32 chain positions: min (face << 32 | position)
+    const int tid = threadIdx.x;
+    const int n = 2 * S;
+    const unsigned long long keep = keep_policy();
+    int open_links = 0;
+    for (int i = tid; i < S; i += kWalkThreads) {
+        const int a = ld_keep(&w.seg_link[2ll * off + 2 * i], keep), b = ld_keep(&w.seg_link[2ll * off + 2 * i + 1], keep);
+        open_links |= (a < 0) | (b < 0);
+        const int f = ld_keep(&w.seg_face[off + i], keep);
+        NX[2 * i] = b < 0 ? kNone : (unsigned short)(b - 2 * off);        // next(2i)   = link[2i + 1]
+        NX[2 * i + 1] = a < 0 ? kNone : (unsigned short)(a - 2 * off);    // next(2i+1) = link[2i]
+        V[2 * i] = 2 * f;
+        V[2 * i + 1] = 2 * f + 1;
+    }
+    if (tid == 0) { s_nloops = 0; s_npaths = 0; }
+    const bool mixed = __syncthreads_or(open_links) != 0;
+
+    // in-place doubling round: read phase -> barrier -> write phase -> barrier.  MODE 0: distance to the dead end
+    // (dead ends are self loops with distance 0); MODE 1: cycle minimum of V and distance to it (open states skipped).
+    auto doubling = [&](auto mode_tag) {
+        constexpr int MODE = decltype(mode_tag)::value;
+        for (int step = 1; step < S; step <<= 1) {
+            unsigned int njd[kRankPerThread];   // new jump pointer (low half) and distance (high half)
+            int nv[kRankPerThread];
+#pragma unroll
+            for (int q = 0; q < kRankPerThread; ++q) {
+                if (q * kWalkThreads >= n) break;   // uniform
+                const int e = tid + q * kWalkThreads;
+                if (e < n) {
+                    if (MODE == 0) {
+                        const int j = J[e];
+                        njd[q] = (unsigned int)J[j] | ((unsigned int)(D[e] + D[j]) << 16);
+                    } else {
+                        const int ve = V[e];
+                        if (ve < 0) { njd[q] = 0u; nv[q] = ve; }   // open state: untouched (its J / D hold a face id)
+                        else {
+                            const int j = J[e];
+                            const unsigned int jj = J[j];
+                            const int vj = V[j];
+                            if (vj < ve) { nv[q] = vj; njd[q] = jj | ((unsigned int)(D[j] + step) << 16); }
+                            else { nv[q] = ve; njd[q] = jj | ((unsigned int)D[e] << 16); }
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int q = 0; q < kRankPerThread; ++q) {
+                if (q * kWalkThreads >= n) break;   // uniform
+                const int e = tid + q * kWalkThreads;
+                if (e < n) {
+                    if (MODE == 0) { J[e] = (unsigned short)(njd[q] & 0xffffu); D[e] = (unsigned short)(njd[q] >> 16); }
+                    else if (nv[q] >= 0) { J[e] = (unsigned short)(njd[q] & 0xffffu); D[e] = (unsigned short)(njd[q] >> 16); V[e] = nv[q]; }
+                }
+            }
+            __syncthreads();
+        }
+    };
+
+    if (mixed) {
+        // ---- pass 1: dead end and distance to it for every state of an open chain --------------------------------------
+        for (int e = tid; e < n; e += kWalkThreads) {
+            const unsigned short nx = NX[e];
+            J[e] = nx == kNone ? (unsigned short)e : nx;
+            D[e] = nx == kNone ? 0 : 1;
+        }
+        __syncthreads();
+        doubling(std::integral_constant<int, 0>{});
+        // open state <=> its jump target is a dead end.  Keep (dead end, distance) in V (sign bit set) and the face id
+        // in the now free (J, D) pair of the state.
+        int vnew[kRankPerThread];
+#pragma unroll
+        for (int q = 0; q < kRankPerThread; ++q) {
+            if (q * kWalkThreads >= n) break;
+            const int e = tid + q * kWalkThreads;
+            if (e < n) {
+                const int t = J[e];
+                vnew[q] = NX[t] == kNone ? (int)(0x80000000u | ((unsigned int)t << 16) | (unsigned int)D[e]) : V[e];
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < kRankPerThread; ++q) {
+            if (q * kWalkThreads >= n) break;
+            const int e = tid + q * kWalkThreads;
+            if (e < n) {
+                const int f = V[e] >> 1;          // V still holds 2 * face + parity
+                if (vnew[q] < 0) { J[e] = (unsigned short)(f & 0xffff); D[e] = (unsigned short)((unsigned int)f >> 16); }
+                V[e] = vnew[q];
+            }
+        }
+        __syncthreads();
+    }
+    // ---- pass 2: closed loops ----------------------------------------------------------------------------------------------
+    for (int e = tid; e < n; e += kWalkThreads) {
+        if (V[e] >= 0) { J[e] = NX[e]; D[e] = 0; }
+    }
+    __syncthreads();
+    doubling(std::integral_constant<int, 1>{});
+    // seed states of closed loops: even states that are their own cycle minimum
+    for (int i = tid; i < S; i += kWalkThreads) {
+        const int e = 2 * i;
+        if (V[e] >= 0 && D[e] == 0 && (V[e] & 1) == 0) {
+            const int slot = atomicAdd(&s_nloops, 1);
+            if (slot < kRankMaxLoops) {
+                s_lface[slot] = V[e] >> 1;
+                s_llen[slot] = (int)D[NX[e]] + 1;    // the state after the seed is length - 1 steps behind it
+                s_linfo[slot] = -1;
+            }
+        }
+    }
+    __syncthreads();
+    if (s_nloops > kRankMaxLoops) return false;
+
+    if (mixed) {
+        // ---- open chains: canonical direction = the one whose dead end has the smaller state id ------------------------
+        auto dead_end = [&](int e) { return (int)(((unsigned int)V[e] >> 16) & 0x3fffu); };
+        auto dist_end = [&](int e) { return (int)((unsigned int)V[e] & 0xffffu); };
+        for (int e = tid; e < n; e += kWalkThreads) {
+            if (V[e] < 0 && NX[e] == kNone && e < dead_end(e ^ 1)) {   // e is the dead end of a canonical direction
+                const int slot = atomicAdd(&s_npaths, 1);
+                if (slot < kRankMaxPaths) { s_pterm[slot] = e; s_plen[slot] = dist_end(e ^ 1) + 1; }
+            }
+        }
+        __syncthreads();
+        const int npaths = s_npaths;
+        if (npaths > kRankMaxPaths) return false;
+        if (tid == 0) { int run = 0; for (int c = 0; c < npaths; ++c) { s_pbase[c] = run; run += s_plen[c]; } }
+        __syncthreads();   // NX is dead from here on: its storage becomes P | Q
+        for (int e = tid; e < n; e += kWalkThreads) {
+            if (V[e] >= 0) continue;
+            const int t = dead_end(e);
+            if (!(t < dead_end(e ^ 1))) continue;                  // the reverse traversal of its chain
+            int c = 0;
+            while (s_pterm[c] != t) ++c;
+            P[s_pbase[c] + dist_end(e ^ 1)] = (unsigned short)e;   // position = distance of the reverse state to ITS dead end
+        }
+        __syncthreads();
+        // faces by chain position, compact (the J array is free: closed loops are done with it, and the face ids that
+        // the open states keep in their (J, D) pairs are read into registers first)
+        int* facepos = reinterpret_cast<int*>(J);
+        {
+            const int total = s_pbase[npaths - 1] + s_plen[npaths - 1];
+            int fr[(kWalkSmemSegs + kWalkThreads - 1) / kWalkThreads];
+#pragma unroll
+            for (int q = 0; q < (kWalkSmemSegs + kWalkThreads - 1) / kWalkThreads; ++q) {
+                const int g = tid + q * kWalkThreads;
+                if (g < total) { const int e = P[g]; fr[q] = (int)((unsigned int)J[e] | ((unsigned int)D[e] << 16)); }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int q = 0; q < (kWalkSmemSegs + kWalkThreads - 1) / kWalkThreads; ++q) {
+                const int g = tid + q * kWalkThreads;
+                if (g < total) facepos[g] = fr[q];
+            }
+            __syncthreads();
+            // minima of aligned 32-position chunks: inside the unused interval of a chain they never change, so the
+            // arg-min of a piece reads two partial chunks and a few chunk minima instead of the whole interval
+            for (int c = tid >> 5; 32 * c < total; c += kWalkThreads / 32) {
+                const int g = 32 * c + (tid & 31);
+                unsigned long long key = g < total ? (((unsigned long long)(unsigned int)facepos[g] << 32) | (unsigned int)g) : ~0ull;
+                for (int o = 16; o > 0; o >>= 1) {
+                    const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+                    key = other < key ? other : key;
+                }
+                if ((tid & 31) == 0) s_cmin[c] = key;
+            }
+        }
+        // replay the seed order on intervals: one WARP per chain (chains are independent; no block-wide barrier per piece)
+        if (tid == 0) s_slot = 0;   // overflow flag
+        __syncthreads();
+
+        const int lane = tid & 31;
+        for (int c = tid >> 5; c < npaths; c += kWalkThreads / 32) {
+            const int base = s_pbase[c];
+            int lo = 0, hi = s_plen[c] - 1;
+            while (lo <= hi) {
+                // arg-min of the face id over the interval: two partial 32-position chunks + the chunk minima between
+                unsigned int bf = 0xffffffffu;   // this lane's best face and its global position
+                int bg = 0;
+                {
+                    const int glo = base + lo, ghi = base + hi;
+                    const int c_lo = glo >> 5, c_hi = ghi >> 5;
+                    int g = 32 * c_lo + lane;
+                    if (g >= glo && g <= ghi) { bf = (unsigned int)facepos[g]; bg = g; }
+                    if (c_hi > c_lo) {
+                        g = 32 * c_hi + lane;
+                        if (g <= ghi) { const unsigned int f = (unsigned int)facepos[g]; if (f < bf) { bf = f; bg = g; } }
+                        for (int c2 = c_lo + 1 + lane; c2 < c_hi; c2 += 32) {
+                            const unsigned long long key = s_cmin[c2];
+                            const unsigned int f = (unsigned int)(key >> 32);
+                            if (f < bf) { bf = f; bg = (int)(key & 0xffffffffu); }
+                        }
+                    }
+                }
+                const unsigned int fmin = __reduce_min_sync(0xffffffffu, bf);       // face ids are unique: one owner
+                const int owner = __ffs(__ballot_sync(0xffffffffu, bf == fmin)) - 1;
+                const int pmin = __shfl_sync(0xffffffffu, bg, owner) - base;
+                const int e = P[base + pmin];
+                const bool reverse = (e & 1) != 0;   // the seed's p1 -> p2 traversal runs against the canonical direction
+                const int a0 = reverse ? lo : pmin, a1 = reverse ? pmin : hi;
+                int slot = 0;
+                if (lane == 0) slot = atomicAdd(&s_nloops, 1);
+                slot = __shfl_sync(0xffffffffu, slot, 0);
+                if (slot >= kRankMaxLoops) { s_slot = 1; break; }
+                if (lane == 0) {
+                    s_lface[slot] = (int)fmin;
+                    s_llen[slot] = a1 - a0 + 1;
+                    s_linfo[slot] = ((base + pmin) << 1) | (reverse ? 1 : 0);
+                }
+                for (int pp = a0 + lane; pp <= a1; pp += 32) Q[base + pp] = (unsigned short)slot;
+                if (reverse) lo = pmin + 1; else hi = pmin - 1;
+            }
+        }
+        __syncthreads();
+        if (s_slot) return false;
+    }
+    const int C = s_nloops;
+    // order by seed face (counting rank; C is small), row bases by a serial prefix over the sorted pieces
+    for (int c = tid; c < C; c += kWalkThreads) {
+        const int f = s_lface[c];
+        int r = 0;
+        for (int o = 0; o < C; ++o) r += s_lface[o] < f;
+        s_sface[r] = f;
+        s_slen[r] = s_llen[c];
+        s_lbase[c] = r;            // rank for now
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int run = 0;
+        for (int c = 0; c < C; ++c) { s_sbase[c] = run; run += s_slen[c] + 1; }
+        nums[k] = C;
+        w.rows_used[k] = min(run, nF);
+    }
+    __syncthreads();
+    for (int c = tid; c < C; c += kWalkThreads) s_lbase[c] = s_sbase[s_lbase[c]];
+    __syncthreads();
+    // ---- every state of a walked direction writes its row -------------------------------------------------------------------
+    const float* pts = w.seg_pts + 6ll * off;
+    float* out = merged + (size_t)k * nF * 3;
+    auto emit_row = [&](int row, int endpoint) {
+        if (row < nF) {
+            const float* q = pts + 3ll * endpoint;
+            out[3ll * row] = ld_keep(q, keep); out[3ll * row + 1] = ld_keep(q + 1, keep); out[3ll * row + 2] = ld_keep(q + 2, keep);
+        }
+    };
+    auto emit_separator = [&](int row) {
+        if (row < nF) { float* sp = out + 3ll * row; sp[0] = -1e9f; sp[1] = -1e9f; sp[2] = -1e9f; }
+    };
+    for (int e = tid; e < n; e += kWalkThreads) {
+        const int key = V[e];
+        if (key < 0 || (key & 1)) continue;          // open chain (below) / the reverse traversal of its loop
+        const int f = key >> 1;
+        int lo = 0, hi = C - 1;                      // piece index: position of f among the sorted seed faces
+        while (lo < hi) { const int m = (lo + hi) >> 1; if (s_sface[m] < f) lo = m + 1; else hi = m; }
+        const int len = s_slen[lo], base = s_sbase[lo];
+        const int d = D[e];
+        const int r = d == 0 ? 0 : len - d;          // segments walked before this one
+        emit_row(base + r, r == 0 ? e : (e ^ 1));
+        if (r == 0) emit_separator(base + len);
+    }
+    if (mixed) {
+        const int total = s_npaths > 0 ? s_pbase[s_npaths - 1] + s_plen[s_npaths - 1] : 0;
+        for (int g = tid; g < total; g += kWalkThreads) {
+            const int e = P[g];                      // canonical state of the segment at chain position g
+            const int piece = Q[g];
+            const int info = s_linfo[piece];
+            const int seed_pos = info >> 1;
+            const bool reverse = info & 1;
+            const int r = reverse ? seed_pos - g : g - seed_pos;
+            const int base = s_lbase[piece];
+            // rank 0: the seed's p1 (its even endpoint); rank >= 1: the endpoint the segment is left through
+            emit_row(base + r, r == 0 ? (e & ~1) : (reverse ? e : (e ^ 1)));
+            if (r == 0) emit_separator(base + s_llen[piece]);
+        }
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(kWalkThreads, 2)
+contour_walk_kernel(int nF, ContourWs w, float* __restrict__ merged, int* __restrict__ nums) {
+    extern __shared__ int s_dyn[];
+    const int k = blockIdx.x;
+    const long long t_begin = clock64();
+    struct Stamp { int* slot; long long t0; __device__ ~Stamp() { if (threadIdx.x == 0) *slot = (int)(clock64() - t0); } } stamp{&w.cursor[k], t_begin};
+    const bool overflow = w.hdr[0] != 0;
+    const int S = overflow ? 0 : w.seg_count[k];
+    const int off = w.seg_offset[k];
+    if (S == 0) {
+        if (threadIdx.x == 0) { nums[k] = 0; w.rows_used[k] = 0; }
+        return;
+    }
+    // Working set of the chain walk: partner links (local endpoint ids), the row order being recorded and the
+    // per-segment consumed flags.  In shared memory when the isovalue fits (no global traffic on the chain, which
+    // matters because the zero fill saturates HBM concurrently), in the workspace otherwise.
+    if (S <= kWalkSmemSegs) {
+        if (walk_ranked(S, off, nF, k, w, reinterpret_cast<unsigned char*>(s_dyn), merged, nums)) return;
+        __syncthreads();
+        if (threadIdx.x == 0) atomicAdd(&w.hdr[8], 1);   // statistics: isovalues walked serially
+        unsigned short* nx = reinterpret_cast<unsigned short*>(s_dyn);
+        unsigned short* order = nx + 2 * kWalkSmemSegs;
+        int* face = reinterpret_cast<int*>(order + 2 * kWalkSmemSegs);
+        unsigned char* used = reinterpret_cast<unsigned char*>(face + kWalkSmemSegs);
+        walk_isovalue<unsigned short, unsigned char>(S, off, nF, k, w, nx, order, used, face, nullptr, merged, nums);
+    } else {
+        // the hash-slot array is dead after `link`: reuse it as int flags
+        walk_isovalue<int, int>(S, off, nF, k, w, w.seg_link + 2ll * off, w.seg_order + 2ll * off, w.seg_slot + 2ll * off,
+                                nullptr, nullptr, merged, nums);
     }
 }
 
@@ -533,10 +943,16 @@ int inf3dp_extract_isocontours(const float* V, const int32_t* F, const float* fi
     if (rc != INF3DP_OK) return rc;
     // developer instrumentation (INF3DP_CONTOUR_DEBUG=1): per-phase CUDA-event timeline on both streams
     static const bool debug = getenv("INF3DP_CONTOUR_DEBUG") != nullptr;
+    static const int dev_skip = getenv("INF3DP_CONTOUR_SKIP") ? atoi(getenv("INF3DP_CONTOUR_SKIP")) : 0;  // 1: no fill, 2: no chain
     cudaEvent_t dbg_ev[8] = {nullptr};
     if (debug) for (int i = 0; i < 8; ++i) cudaEventCreate(&dbg_ev[i]);
     auto mark = [&](int i, cudaStream_t s_) { if (debug) cudaEventRecord(dbg_ev[i], s_); };
     mark(0, st);
+
+    const int sms = num_sms();
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    INF3DP_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    INF3DP_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
 
     contour_prep_kernel<<<1, 1024, 0, st>>>(iso, K, w);
     INF3DP_LAUNCH_CHECK("contour_prep_kernel");
@@ -551,14 +967,10 @@ int inf3dp_extract_isocontours(const float* V, const int32_t* F, const float* fi
 
     // fork: the chain (hash/link/walk) goes to the high-priority helper stream, the bulk zero fill stays on the
     // caller's stream; join before the tail fill (which needs the row counts the walk produced)
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    INF3DP_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
-    INF3DP_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
     INF3DP_CUDA(cudaEventRecord(ev_fork, st));
     mark(1, st);
     INF3DP_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
-    const int sms = num_sms();
-    if (nF > 0) {
+    if (nF > 0 && dev_skip != 2) {
         contour_hash_clear_kernel<<<sms * 4, 256, 0, side>>>(w);
         INF3DP_LAUNCH_CHECK("contour_hash_clear_kernel");
         contour_faces_kernel<true><<<fblocks, kFaceThreads, fsmem, side>>>(V, F, fields, nV, nF, K, w);
@@ -570,13 +982,13 @@ int inf3dp_extract_isocontours(const float* V, const int32_t* F, const float* fi
     }
     INF3DP_CUDA(cudaFuncSetAttribute(contour_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      kWalkSmemBytes));
-    contour_walk_kernel<<<K, kWalkThreads, kWalkSmemBytes, side>>>(nF, w, merged, nums);
+    if (dev_skip != 2) contour_walk_kernel<<<K, kWalkThreads, kWalkSmemBytes, side>>>(nF, w, merged, nums);
     INF3DP_LAUNCH_CHECK("contour_walk_kernel");
     INF3DP_CUDA(cudaEventRecord(ev_join, side));
     mark(6, side);
 
     mark(2, st);
-    if (nF > 0) {
+    if (nF > 0 && dev_skip != 1) {
         // Many SHORT blocks (each thread streams ~16 float4 stores): SM slots free up continuously, so the
         // higher-priority chain kernels on the helper stream are dispatched between them.  (Measured alternatives:
         // a persistent 2-CTA/SM fill cannot keep enough stores in flight -- 3.8 TB/s instead of 6.1 TB/s.)
@@ -602,6 +1014,18 @@ int inf3dp_extract_isocontours(const float* V, const int32_t* F, const float* fi
         cudaStreamSynchronize(st);
         float t[8] = {0};
         for (int i = 1; i < 8; ++i) cudaEventElapsedTime(&t[i], dbg_ev[0], dbg_ev[i]);
+        int hdr_host[32] = {0};
+        cudaMemcpy(hdr_host, w.hdr, sizeof(hdr_host), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[inf3dp contour debug] isovalues walked serially (list capacity exceeded or too large): %d of %d\n", hdr_host[8], K);
+        {
+            std::vector<int> cyc(K), cnt(K);
+            cudaMemcpy(cyc.data(), w.cursor, K * sizeof(int), cudaMemcpyDeviceToHost);
+            cudaMemcpy(cnt.data(), w.seg_count, K * sizeof(int), cudaMemcpyDeviceToHost);
+            int kmax = 0; long long sum = 0; int smax = 0;
+            for (int i = 0; i < K; ++i) { if (cyc[i] > cyc[kmax]) kmax = i; sum += cyc[i]; if (cnt[i] > smax) smax = cnt[i]; }
+            fprintf(stderr, "[inf3dp contour debug] walk CTA cycles: mean %.0f, max %d (isovalue %d, S=%d); max S over isovalues %d\n",
+                    (double)sum / (K > 0 ? K : 1), cyc[kmax], kmax, cnt[kmax], smax);
+        }
         fprintf(stderr, "[inf3dp contour debug] us since start: fork %.0f | caller stream: fill start %.0f end %.0f | chain stream: emit end %.0f "
                         "link end %.0f walk end %.0f | tail fill end %.0f\n", t[1] * 1e3, t[2] * 1e3, t[3] * 1e3, t[4] * 1e3,
                 t[5] * 1e3, t[6] * 1e3, t[7] * 1e3);

@@ -91,6 +91,21 @@ def test_open_mesh_and_tiny_and_empty():
     assert np.array_equal(s, so_) and np.array_equal(n, no) and np.array_equal(m, mo)
 
 
+@pytest.mark.parametrize("nu,nv,K,drop,seed", [(120, 60, 40, 0.03, 0), (160, 80, 24, 0.002, 1), (60, 30, 12, 0.4, 2),
+                                               (300, 150, 16, 0.01, 3)])
+def test_randomly_torn_meshes_open_chains(nu, nv, K, drop, seed):
+    """Faces removed at random: open chains of every length, several chains and many pieces per isovalue (the
+    interval replay of the parallel walk; with 40 % of the faces gone also its capacity fallback to the serial walk)."""
+    V, F = co.torus_mesh(nu, nv)
+    f = _field(V)
+    rng = np.random.default_rng(seed)
+    F2 = np.ascontiguousarray(F[rng.random(len(F)) >= drop])
+    iso = np.linspace(f.min(), f.max(), K).astype(np.float32)
+    mo, no, so_ = co.extract_isocontours(V, F2, f, iso)
+    m, n, s = _run(V, F2, f, iso)
+    assert_equivalent(m, n, s, mo, no, so_)
+
+
 def test_full_size_properties():
     """F = 0.5 M faces, K = 200: properties that hold at any size (no O(S^2) oracle here): rows used = S_k + C_k,
     zero padding, every long loop closes, determinism."""
