@@ -146,7 +146,7 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": "points/s", "cores": cores, "kind": "port", "sample": desc},
             "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "torch": torch.__version__}
-    print(json.dumps(line), flush=True)
+    emit_json_line(line)
 
 
 def bench_isocontours(dev, peaks):
@@ -196,6 +196,40 @@ def bench_isocontours(dev, peaks):
                          "bytes_contract": contract, "bytes_useful": useful,
                          "useful_gbs": useful / (ms / 1e3) / 1e9, "peak_source": peaks["source"]},
             "gpu_launches_per_call": 9}
+
+
+def bench_hessian_sweep(net, dev, peaks):
+    """BASELINE.json configs[4]: synthetic 16M-point sweep with Hessian for the min-curvature field (SURVEY.md 8d cfg 5):
+    value + gradient + Hessian from the tensor-core second-order jet, then the closed-form principal curvatures."""
+    import torch
+    import inf3dp
+    n = 16_777_216
+    g = torch.Generator(device="cpu").manual_seed(0)
+    chunk = 1 << 22
+    x = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    for h in range(0, n, chunk):   # ~U([-1,1]^3), generated on the host generator of SURVEY.md cfg 5 in pieces
+        x[h:h + chunk] = (torch.rand((min(chunk, n - h), 3), generator=g) * 2 - 1).to(dev)
+
+    def sweep():
+        y, J, H = net.query(x, order=2)
+        return inf3dp.principal_curvatures(J[:, 0], H[:, 0])
+    for _ in range(2):
+        sweep()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    iters = 3
+    e0.record()
+    for _ in range(iters):
+        kap, dirs = sweep()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / iters
+    flop = 3_938_816   # SURVEY.md 8d: Hessian mode, 1 + 3 + 6 jet columns
+    tf = n * flop / (ms / 1e3) / 1e12
+    return {"metric": "siren_value_grad_hessian_curvature_points_per_s", "value": n / (ms / 1e3), "unit": "points/s",
+            "ms_per_sweep": ms, "points": n, "kernel": "siren_rev_kernel<CTAS=2,KIND=1> (forward-mode second-order jet) + principal_curvatures_kernel",
+            "flop_per_point": flop, "achieved_tflops": tf, "frac_of_sustained_peak": tf / peaks["tf_sustained"],
+            "checksum": float(kap[:: n // 4096].double().sum())}
 
 
 def run_ours(args):
@@ -305,6 +339,7 @@ def run_ours(args):
         # the jet kernel runs ~0.5-1 s per launch under the power cap: the sustained cuBLAS figure is the fair peak
         peak = peaks["tf_sustained"]
         iso = bench_isocontours(dev, peaks)
+        hess = bench_hessian_sweep(net, dev, peaks)
         cores = os.cpu_count() or 1
         cpu_base = None
         if world == 1:   # reported baseline: rank 0 at N=1 only (torchrun pins OMP threads to 1 for N>1)
@@ -336,15 +371,33 @@ def run_ours(args):
                          "reverse_mode_flop_per_point": FLOP_REVERSE_MODE},
             "cpu_baseline": cpu_base,
             "isocontour": iso,
+            "hessian_sweep": hess,
             "clocks": clocks,
             "torch": torch.__version__,
         }
-        print(json.dumps(line), flush=True)
+        emit_json_line(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit_json_line(line):
+    """The one JSON line goes to the real stdout; everything else the process prints (NCCL banners, library chatter)
+    was redirected to stderr at start-up so that stdout carries exactly one line."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)   # C-level stdout (e.g. "NCCL version ...") -> stderr
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)

@@ -235,15 +235,19 @@ int inf3dp_siren_jet_ws(const void* packed, const float* x, int64_t n, int order
     cudaStream_t st = (cudaStream_t)stream;
     const bool tc_capable = h.tc_ok && order <= 1;
     const bool rev_capable = h.rev_ok && order == 1;
+    const bool jet2_capable = h.rev_ok && order == 2;   // single-output sine network: Hessian on the tensor cores
     const bool have_ws = workspace != nullptr && workspace_bytes >= siren_rev_workspace_bytes();
     switch (mode) {
         case INF3DP_MODE_AUTO:
             if (rev_capable && have_ws) return siren_rev_launch(packed, h, x, n, y, J, workspace, workspace_bytes, st);
+            if (jet2_capable) return siren_jet2_launch(packed, h, x, n, y, J, H, st);
             if (tc_capable) return siren_tc_launch(packed, h, x, n, order, y, J, true, st);
             return siren_simt_launch(packed, h, x, n, order, y, J, H, st);
         case INF3DP_MODE_SIMT:
             return siren_simt_launch(packed, h, x, n, order, y, J, H, st);
         case INF3DP_MODE_TC_PRECISE:
+            if (jet2_capable) return siren_jet2_launch(packed, h, x, n, y, J, H, st);
+            /* fallthrough */
         case INF3DP_MODE_TC_FAST:
             INF3DP_CHECK_ARG(tc_capable, "siren_jet: tensor-core engine needs sine, in=3, hidden=256, 3 hidden layers, "
                              "out<=4 and order<=1");

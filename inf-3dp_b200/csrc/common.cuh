@@ -130,5 +130,7 @@ int siren_rev_pack(const float* const* W, float omega0, const uint32_t* maxabs_b
                    SirenHeader& hdr, cudaStream_t stream);
 int siren_rev_launch(const void* packed, const SirenHeader& h, const float* x, int64_t n, float* y, float* J, void* ws,
                      size_t ws_bytes, cudaStream_t stream);
+int siren_jet2_launch(const void* packed, const SirenHeader& h, const float* x, int64_t n, float* y, float* J, float* H,
+                      cudaStream_t stream);
 
 }  // namespace inf3dp

@@ -77,12 +77,18 @@ struct RevCfg {
     static_assert(kSmemTotal <= 232448 - 1024, "shared memory budget");
 };
 
-template <int CTAS>
+// KIND 0: reverse-mode value + gradient (6 GEMMs per tile of 128 points).
+// KIND 1: forward-mode second-order jet, value + gradient + Hessian (diff_operators.py:27-44 hessian3d): 3 GEMMs per tile
+//         of 12 points x 10 jet rows (value, d/dx_i, d2/dx_i dx_j for ij in 00 01 02 11 12 22; 3 points per 32-lane
+//         quadrant of tensor memory, lanes 30 and 31 idle), same CTA-pair schedule, same weight images (GEMMs 0..2).
+template <int CTAS, int KIND>
 __global__ void __launch_bounds__(kThreads, 1)
 siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __restrict__ x, int64_t n,
-                 float* __restrict__ y, float* __restrict__ J, float4* __restrict__ stash,
+                 float* __restrict__ y, float* __restrict__ J, float* __restrict__ Hout, float4* __restrict__ stash,
                  unsigned long long* __restrict__ dbg) {
     using C = RevCfg<CTAS>;
+    constexpr int kGemms = KIND == 0 ? 6 : 3;
+    constexpr int kTilePts = KIND == 0 ? 128 : 12;
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t sbase = (smem_u32(smem_dyn) + 1023u) & ~1023u;   // same offset in both CTAs of a pair
     unsigned char* sptr = smem_dyn + (sbase - smem_u32(smem_dyn));
@@ -94,7 +100,7 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
     const char* tc = packed + h.off_tc;     // inverse scales live in the forward engine's section
     const char* rv = packed + h.off_rev;
 
-    const int64_t num_tiles = (n + 127) / 128;
+    const int64_t num_tiles = (n + kTilePts - 1) / kTilePts;
     const int64_t num_units = (num_tiles + CTAS - 1) / CTAS;               // work unit = one tile per CTA of the pair
     const int64_t unit0 = blockIdx.x / CTAS, unit_stride = gridDim.x / CTAS;
     const int my_units = (int)((num_units - unit0 + unit_stride - 1) / unit_stride);
@@ -151,7 +157,7 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
             for (int it = 0; it < my_units; ++it) {
-                for (int g = 0; g < 6; ++g) {
+                for (int g = 0; g < kGemms; ++g) {
                     const char* img = rv + kRevOffImg + (size_t)g * kGemmImgBytes;
                     for (int r = 0; r < 4; ++r) {
                         mbar_wait(bar(C::kBarWEmpty + stage), phase ^ 1u);
@@ -177,7 +183,7 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
             unsigned long long wait_a = 0, wait_w = 0;
             const long long t_begin = clock64();
             for (int it = 0; it < my_units; ++it) {
-                for (int g = 0; g < 6; ++g) {
+                for (int g = 0; g < kGemms; ++g) {
                     const uint32_t regA = (g & 1) ? regionQ : regionP;
                     const uint32_t regD = (g & 1) ? regionP : regionQ;
 #pragma unroll
@@ -234,7 +240,7 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
             // ================= peer CTA: forward "my half of the stage has landed" to the leader =====================
             uint32_t stage = 0, phase = 0;
             for (int it = 0; it < my_units; ++it) {
-                for (int gr = 0; gr < 24; ++gr) {
+                for (int gr = 0; gr < 4 * kGemms; ++gr) {
                     mbar_wait(bar(C::kBarWFull + stage), phase);
                     mbar_arrive_cluster(mapa_rank(bar(C::kBarWFull + stage), 0));
                     if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
@@ -267,6 +273,112 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
             if (lane == 0) { if (CTAS == 2) mbar_arrive_cluster(a_ready_addr[mi]); else mbar_arrive(a_ready_addr[mi]); }
         };
 
+        if constexpr (KIND == 1) {
+        // ---------------- second-order forward jet: 3 points x 10 rows per quadrant ------------------------------------------
+        const int pl = lane / 10;                       // point of the quadrant (3 = idle lanes 30, 31)
+        const int c = lane - 10 * pl;                   // jet row: 0 value, 1..3 d/dx_i, 4..9 d2/dx_i dx_j
+        const bool live = lane < 30;
+        int ii = 0, jj = 0;                             // derivative directions of this row
+        if (c >= 1 && c <= 3) { ii = c - 1; jj = c - 1; }
+        else if (c >= 4) { const int q = c - 4; ii = q < 3 ? 0 : (q < 5 ? 1 : 2); jj = q < 3 ? q : (q < 5 ? q - 2 : 2); }
+        const int src_z = 10 * pl, src_i = 10 * pl + 1 + ii, src_j = 10 * pl + 1 + jj;   // lanes holding z, dz_i, dz_j
+        constexpr float kR2 = 0.0625f;                  // second-order rows are carried scaled by 2^-4 (FP16 range)
+        const float sel_v = (live && c == 0) ? 1.f : 0.f, sel_1 = (live && c >= 1 && c <= 3) ? 1.f : 0.f,
+                    sel_2 = (live && c >= 4) ? 1.f : 0.f;
+        const float* s_w0f = reinterpret_cast<const float*>(sptr + C::kSmemW0);
+        for (int it = 0; it < my_units; ++it) {
+            const int64_t tile = (unit0 + (int64_t)it * unit_stride) * CTAS + rank;
+            const int64_t pt = tile * kTilePts + 3 * quad + pl;
+            const bool pvalid = live && pt < n;
+            float px = 0.f, py = 0.f, pz = 0.f;
+            if (pvalid) { px = x[3 * pt]; py = x[3 * pt + 1]; pz = x[3 * pt + 2]; }
+            // ---- layer 0 (FP32): a = sin z, da_i = cos z w_i, d2a_ij = -sin z w_i w_j ------------------------------------
+#pragma unroll 1
+            for (int mi = 0; mi < 4; ++mi) {
+                const int m = grp + 4 * mi;
+                uint32_t o[16];
+#pragma unroll
+                for (int i = 0; i < 16; i += 2) {
+                    float r2[2];
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const int f = 16 * m + i + u;
+                        const float4 w = s_w0[f];
+                        const float z0 = fmaf(w.z, pz, fmaf(w.y, py, fmaf(w.x, px, w.w)));
+                        const float sn = sin_layer0(z0), cn = cos_mufu(z0);
+                        const float wi = s_w0f[4 * f + ii], wj = s_w0f[4 * f + jj];
+                        r2[u] = sel_v * sn + sel_1 * cn * wi - (sel_2 * kR2) * sn * wi * wj;
+                    }
+                    split_pack<true>(r2[0], r2[1], o[i >> 1], o[8 + (i >> 1)]);
+                }
+                TC_ST16(regionP + lane_off + 16u * (uint32_t)m, o);
+                publish(mi);
+            }
+            float acc = 0.f;
+#pragma unroll
+            for (int g = 0; g < 3; ++g) {
+                const uint32_t regD = (g & 1) ? regionP : regionQ;
+                const float inv = s_misc[g];
+                // out = [value] sin z  +  [first, second] cos z * (own / S)  -  [second] 2^-4 sin z (dz_i / S)(dz_j / S)
+                const float kb = (sel_1 + sel_2) * inv, kc = -(sel_2 * kR2) * inv * inv;
+                mbar_wait_warp(bar(C::kBarDFull), dphase, lane, pd);
+                dphase ^= 1u;
+                tc_fence_after();
+                uint32_t v[16];
+                TC_LD16(regD + lane_off + 16u * (uint32_t)grp, v);
+#pragma unroll 1
+                for (int mi = 0; mi < 4; ++mi) {
+                    const int m = grp + 4 * mi;
+                    const uint32_t addr = regD + lane_off + 16u * (uint32_t)m;
+                    tc_wait_ld();
+                    float cur[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) cur[i] = __uint_as_float(v[i]);
+                    if (mi < 3) TC_LD16(addr + 64u, v);
+                    const float4* bp = reinterpret_cast<const float4*>(s_bias + g * 256 + 16 * m);
+                    float outv[16];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 b = bp[q];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int i = 4 * q + u;
+                            const float own = cur[i];
+                            const float dv = __shfl_sync(0xffffffffu, own, src_z);
+                            const float di = __shfl_sync(0xffffffffu, own, src_i);
+                            const float dj = __shfl_sync(0xffffffffu, own, src_j);
+                            const float z = fmaf(dv, inv, u == 0 ? b.x : (u == 1 ? b.y : (u == 2 ? b.z : b.w)));
+                            const float sn = sin_mufu(z), cn = cos_mufu(z);
+                            outv[i] = fmaf(sel_v, sn, fmaf(kb * cn, own, (kc * sn) * (di * dj)));
+                        }
+                    }
+                    if (g < 2) {
+                        uint32_t o[16];
+#pragma unroll
+                        for (int i = 0; i < 16; i += 2) split_pack<true>(outv[i], outv[i + 1], o[i >> 1], o[8 + (i >> 1)]);
+                        TC_ST16(addr, o);
+                        publish(mi);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) acc = fmaf(outv[i], s_w4[16 * m + i].x, acc);   // linear output layer (FP32)
+                    }
+                }
+            }
+            // ---- outputs: sum the four feature-quarter partials of every jet row in a fixed order -----------------------
+            s_part[grp * 128 + row] = acc;
+            asm volatile("bar.sync 1, 512;" ::: "memory");
+            if (grp == 0 && pvalid) {
+                const float val = ((s_part[row] + s_part[128 + row]) + s_part[256 + row]) + s_part[384 + row];
+                if (c == 0) y[pt] = val + s_misc[3];
+                else if (c <= 3) J[3 * pt + (c - 1)] = val;
+                else {
+                    const float hv = val * (1.f / kR2);
+                    Hout[9 * pt + 3 * ii + jj] = hv;
+                    Hout[9 * pt + 3 * jj + ii] = hv;
+                }
+            }
+        }
+        } else {
         for (int it = 0; it < my_units; ++it) {
             const int64_t tile = (unit0 + (int64_t)it * unit_stride) * CTAS + rank;
             const int64_t pt = tile * 128 + row;
@@ -412,6 +524,7 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
             // reading (tcgen05.wait::ld above); s_part is rewritten only after six more d_full phases, which need every
             // epilogue warp (including the readers) to have published its next layer-0 slices.
         }
+        }
         if (dbg && blockIdx.x == 0 && lane == 0) dbg[8 + warp] = wait_d;
     }
 
@@ -466,14 +579,15 @@ __global__ void rev_pack_out_kernel(const float* __restrict__ W4, const uint32_t
     if (f < 256) reinterpret_cast<float2*>(rv + kRevOffW4)[f] = make_float2(W4[f], G * W4[f]);
 }
 
-template <int CTAS>
-int launch_rev(const void* packed, const SirenHeader& h, const float* x, int64_t n, float* y, float* J, void* ws,
+template <int CTAS, int KIND>
+int launch_rev(const void* packed, const SirenHeader& h, const float* x, int64_t n, float* y, float* J, float* H, void* ws,
                cudaStream_t stream) {
     using C = RevCfg<CTAS>;
-    auto kern = siren_rev_kernel<CTAS>;
+    auto kern = siren_rev_kernel<CTAS, KIND>;
     const int smem = (int)C::kSmemTotal + 1024;
     INF3DP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    const int64_t tiles = (n + 127) / 128;
+    constexpr int kTilePts = KIND == 0 ? 128 : 12;
+    const int64_t tiles = (n + kTilePts - 1) / kTilePts;
     const int64_t units = (tiles + CTAS - 1) / CTAS;
     const int64_t max_units = num_sms() / CTAS;
     const int grid = (int)(units < max_units ? units : max_units) * CTAS;
@@ -495,7 +609,7 @@ int launch_rev(const void* packed, const SirenHeader& h, const float* x, int64_t
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    INF3DP_CUDA(cudaLaunchKernelEx(&cfg, kern, (const char*)packed, h, x, n, y, J, (float4*)ws, dbg));
+    INF3DP_CUDA(cudaLaunchKernelEx(&cfg, kern, (const char*)packed, h, x, n, y, J, H, (float4*)ws, dbg));
     INF3DP_LAUNCH_CHECK("siren_rev_kernel");
     if (debug) {
         unsigned long long hbuf[64];
@@ -506,9 +620,9 @@ int launch_rev(const void* packed, const SirenHeader& h, const float* x, int64_t
         for (int g = 0; g < 6; ++g)
             fprintf(stderr, "[inf3dp rev debug] GEMM %d: a_ready wait per round %.0f %.0f %.0f %.0f cyc\n", g, hbuf[32 + g * 4] / u,
                     hbuf[33 + g * 4] / u, hbuf[34 + g * 4] / u, hbuf[35 + g * 4] / u);
-        fprintf(stderr, "[inf3dp rev debug] CTAS=%d block0: %.0f units, %.0f cyc/unit (6 GEMMs); MMA thread blocked on a_ready %.0f, "
+        fprintf(stderr, "[inf3dp rev debug] CTAS=%d KIND=%d block0: %.0f units, %.0f cyc/unit (%d GEMMs); MMA thread blocked on a_ready %.0f, "
                         "on w_full %.0f cyc/unit; epilogue warp0 blocked on d_full %.0f, warp5 %.0f, warp15 %.0f cyc/unit\n",
-                CTAS, u, hbuf[0] / u, hbuf[1] / u, hbuf[2] / u, hbuf[8] / u, hbuf[13] / u, hbuf[23] / u);
+                CTAS, KIND, u, hbuf[0] / u, KIND == 0 ? 6 : 3, hbuf[1] / u, hbuf[2] / u, hbuf[8] / u, hbuf[13] / u, hbuf[23] / u);
     }
     return INF3DP_OK;
 }
@@ -543,7 +657,17 @@ int siren_rev_launch(const void* packed, const SirenHeader& h, const float* x, i
                      "siren_rev: workspace of %zu bytes needed (inf3dp_siren_jet_workspace_bytes), got %zu",
                      siren_rev_workspace_bytes(), ws_bytes);
     static const int ctas = [] { const char* e = getenv("INF3DP_REV_CTAS"); return e && atoi(e) == 1 ? 1 : 2; }();
-    return ctas == 1 ? launch_rev<1>(packed, h, x, n, y, J, ws, stream) : launch_rev<2>(packed, h, x, n, y, J, ws, stream);
+    return ctas == 1 ? launch_rev<1, 0>(packed, h, x, n, y, J, nullptr, ws, stream)
+                     : launch_rev<2, 0>(packed, h, x, n, y, J, nullptr, ws, stream);
+}
+
+// Value + gradient + Hessian (order 2) of single-output networks: forward-mode second-order jet on the CTA-pair engine.
+int siren_jet2_launch(const void* packed, const SirenHeader& h, const float* x, int64_t n, float* y, float* J, float* H,
+                      cudaStream_t stream) {
+    INF3DP_CHECK_ARG(h.rev_ok && h.off_rev != 0, "siren_jet2: packed weights carry no CTA-pair operand images");
+    static const int ctas = [] { const char* e = getenv("INF3DP_REV_CTAS"); return e && atoi(e) == 1 ? 1 : 2; }();
+    return ctas == 1 ? launch_rev<1, 1>(packed, h, x, n, y, J, H, nullptr, stream)
+                     : launch_rev<2, 1>(packed, h, x, n, y, J, H, nullptr, stream);
 }
 
 }  // namespace inf3dp

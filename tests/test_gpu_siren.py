@@ -57,11 +57,14 @@ def test_value_only_and_quaternion_out4(golden, engine):
         assert so.angle_deg(J1.cpu().numpy()[:, c], Jr[:, c]).max() <= TOL_ANGLE
 
 
-def test_hessian_and_curvature_vs_reference(golden):
+@pytest.mark.parametrize("engine", ["simt", "tc_precise", "auto"])
+def test_hessian_and_curvature_vs_reference(golden, engine):
+    """hessian3d / min_max_curvs_and_vectors of the reference (diff_operators.py:27-44, :167-220) vs the order-2 jet:
+    FP32 CUDA-core engine and the tensor-core second-order jet (CTA pairs, 10 jet rows per point)."""
     import inf3dp
     net = _net(golden)
     x = torch.from_numpy(golden["sdf/hess_x"]).cuda()
-    y, J, H = net.query(x, order=2, mode="simt")
+    y, J, H = net.query(x, order=2, mode=engine)
     Hn = H.cpu().numpy()
     ref = golden["sdf/hess3d"]
     rel = np.linalg.norm((Hn - ref).reshape(len(Hn), -1), axis=1) / np.linalg.norm(ref.reshape(len(ref), -1), axis=1)
@@ -224,3 +227,28 @@ def test_slice_field_vs_reference_golden(golden, engine):
     y, J, _ = net.query(x, order=1, mode=engine)
     assert np.abs(y.cpu().numpy() - golden["slice/y"]).max() <= TOL_F
     assert so.angle_deg(J.cpu().numpy()[:, 0], golden["slice/grad"]).max() <= TOL_ANGLE
+
+
+@pytest.mark.parametrize("n", [1, 11, 12, 13, 24, 25, 1000, 50021])
+def test_order2_tensor_engine_ragged_sizes_vs_oracle(golden, n):
+    """Tensor-core Hessian engine on ragged batch sizes (tiles are 12 points per CTA, 24 per CTA pair) against the
+    fp64 oracle: value / gradient at the north_star tolerances, Hessian relative Frobenius <= 1e-3 (proposed tolerance,
+    SURVEY.md 8c; measured ~3e-5), exact symmetry, batch-split invariance."""
+    net = _net(golden)
+    g = torch.Generator().manual_seed(100 + n)
+    x = (torch.rand(n, 3, generator=g) * 2 - 1).cuda()
+    y, J, H = net.query(x, order=2, mode="tc_precise")
+    assert y.shape == (n, 1) and J.shape == (n, 1, 3) and H.shape == (n, 1, 3, 3)
+    m = min(n, 4096)
+    yo, Jo, Ho = so.siren_jet(layers_from_golden(golden, "sdf"), x[:m].cpu().numpy().astype(np.float64), order=2)
+    assert np.abs(y[:m].cpu().numpy() - yo).max() <= TOL_F
+    assert so.angle_deg(J[:m].cpu().numpy()[:, 0], Jo[:, 0]).max() <= TOL_ANGLE
+    Hn = H.cpu().numpy()[:, 0]
+    rel = np.linalg.norm((Hn[:m] - Ho[:, 0]).reshape(m, -1), axis=1) / np.linalg.norm(Ho[:, 0].reshape(m, -1), axis=1)
+    assert rel.max() <= 1e-3
+    assert np.array_equal(Hn, np.swapaxes(Hn, -1, -2))
+    assert torch.isfinite(H).all()
+    if n > 30:
+        k = 17
+        y2, J2, H2 = net.query(x[k:], order=2, mode="tc_precise")
+        assert torch.equal(y2, y[k:]) and torch.equal(J2, J[k:]) and torch.equal(H2, H[k:])
