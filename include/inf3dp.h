@@ -113,6 +113,19 @@ int inf3dp_extract_isocontours(const float* vertices, const int32_t* faces, cons
 int inf3dp_extract_isocontours_status(const void* workspace, int K, int32_t* seg_counts_host,
                                       inf3dp_stream_t stream);
 
+/* Compact variant: the same row streams without the dense zero-padded [K, nF, 3] contract.
+ * Isovalue k's rows (loops separated and terminated by (-1e9,-1e9,-1e9) rows, exactly the first row_counts[k] rows of
+ * contours_merged[k]) are written at rows[row_offsets[k] ...]; row_counts[k] = S_k + C_k, contour_nums[k] = C_k.
+ * `rows` must hold inf3dp_extract_isocontours_compact_rows(...) rows of 3 floats (twice the segment pool of the
+ * workspace); nothing else of it is written.  Replaces the dense device-to-host copy + host scan of
+ * toolpath_utils.py:38-134 (split_merged_contours) by a transfer of the used rows only. */
+int64_t inf3dp_extract_isocontours_compact_rows(int nV, int nF, int K, size_t workspace_bytes);
+int inf3dp_extract_isocontours_compact(const float* vertices, const int32_t* faces, const float* fields,
+                                       const float* iso_values, int nV, int nF, int K, float* rows,
+                                       int64_t rows_capacity, int64_t* row_offsets, int32_t* row_counts,
+                                       int32_t* contour_nums, void* workspace, size_t workspace_bytes,
+                                       inf3dp_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Three-field voxel intersection.  Replaces contour_cuda/ext.cpp:20-46 get_fields_intersection_inter_slice
  * (-> intersection.cu:227-287, kernel :31-224).

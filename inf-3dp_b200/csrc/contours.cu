@@ -53,6 +53,7 @@ struct ContourWs {
     int* hvals;          // [hcap][2]
     int cap;
     int hcap;
+    int compact;         // 1: rows of isovalue k go to merged + 6 * seg_offset[k] (at most 2 S_k rows), no dense contract
     size_t total_bytes;
 };
 
@@ -364,6 +365,14 @@ constexpr int kRankPerThread = 2 * kWalkSmemSegs / kWalkThreads;   // traversal 
 constexpr int kRankMaxLoops = 320;   // contour pieces (closed loops + pieces of open chains) per isovalue
 constexpr int kRankMaxPaths = 32;    // open chains per isovalue
 
+// Where isovalue k's row stream goes, and how many rows fit: the dense [K, F, 3] contract of the reference
+// (isocontours.cu:230-236), or the compact layout (2 S_k rows at 2 * seg_offset[k]; rows used = S_k + C_k <= 2 S_k).
+__device__ __forceinline__ float* row_window(const ContourWs& w, int k, int off, int S, int nF, float* merged, int& limit) {
+    if (w.compact) { limit = 2 * S; return merged + 6ll * off; }
+    limit = nF;
+    return merged + (size_t)k * nF * 3;
+}
+
 template <typename IdxT> struct WalkIdx;
 template <> struct WalkIdx<int> {
     static constexpr int kNone = -1, kSep = -2;
@@ -399,7 +408,8 @@ __device__ __forceinline__ void walk_isovalue(int S, int off, int nF, int k, con
     }
     const int* face = face_copy ? face_copy : w.seg_face + off;
     const float* pts = w.seg_pts + 6ll * off;       // [S][2][3] == flat [endpoint][3]; rows <= S + C <= 2S
-    float* out = merged + (size_t)k * nF * 3;
+    int limit;
+    float* out = row_window(w, k, off, S, nF, merged, limit);
     int row = 0, contours = 0;
     __syncthreads();
     if (by_face != nullptr) {
@@ -477,11 +487,11 @@ __device__ __forceinline__ void walk_isovalue(int S, int off, int nF, int k, con
         if (contours > 0) order[row++] = X::kSep;      // trailing separator (isocontours.cu:205-210)
         nums[k] = contours;
         s_rows = row;
-        w.rows_used[k] = min(row, nF);
+        w.rows_used[k] = min(row, limit);
     }
     __syncthreads();
     // phase 2: all threads gather the points and write the row stream
-    const int rows = min(s_rows, nF);
+    const int rows = min(s_rows, limit);
     for (int r = threadIdx.x; r < rows; r += blockDim.x) {
         const IdxT e = order[r];
         float a = -1e9f, b = -1e9f, c = -1e9f;
@@ -759,22 +769,23 @@ __device__ bool walk_ranked(int S, int off, int nF, int k, const ContourWs& w, u
         int run = 0;
         for (int c = 0; c < C; ++c) { s_sbase[c] = run; run += s_slen[c] + 1; }
         nums[k] = C;
-        w.rows_used[k] = min(run, nF);
+        w.rows_used[k] = min(run, w.compact ? 2 * S : nF);
     }
     __syncthreads();
     for (int c = tid; c < C; c += kWalkThreads) s_lbase[c] = s_sbase[s_lbase[c]];
     __syncthreads();
     // ---- every state of a walked direction writes its row -------------------------------------------------------------------
     const float* pts = w.seg_pts + 6ll * off;
-    float* out = merged + (size_t)k * nF * 3;
+    int limit;
+    float* out = row_window(w, k, off, S, nF, merged, limit);
     auto emit_row = [&](int row, int endpoint) {
-        if (row < nF) {
+        if (row < limit) {
             const float* q = pts + 3ll * endpoint;
             out[3ll * row] = ld_keep(q, keep); out[3ll * row + 1] = ld_keep(q + 1, keep); out[3ll * row + 2] = ld_keep(q + 2, keep);
         }
     };
     auto emit_separator = [&](int row) {
-        if (row < nF) { float* sp = out + 3ll * row; sp[0] = -1e9f; sp[1] = -1e9f; sp[2] = -1e9f; }
+        if (row < limit) { float* sp = out + 3ll * row; sp[0] = -1e9f; sp[1] = -1e9f; sp[2] = -1e9f; }
     };
     for (int e = tid; e < n; e += kWalkThreads) {
         const int key = V[e];
@@ -892,6 +903,15 @@ int get_side_stream(cudaStream_t* out) {
 }
 
 // Largest pool that fits the caller's workspace (>= the default, doubling).
+// compact layout bookkeeping for the caller: row offset / row count of every isovalue
+__global__ void contour_export_kernel(int K, ContourWs w, long long* __restrict__ row_offsets, int* __restrict__ row_counts) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < K) {
+        row_offsets[k] = 2ll * w.seg_offset[k];
+        row_counts[k] = w.hdr[0] != 0 ? 0 : w.rows_used[k];
+    }
+}
+
 int fit_capacity(int nF, int K, size_t ws_bytes) {
     int cap = seg_capacity_default(nF, K);
     const long long worst = (long long)nF * (long long)K;
@@ -1031,6 +1051,58 @@ int inf3dp_extract_isocontours(const float* V, const int32_t* F, const float* fi
                 t[5] * 1e3, t[6] * 1e3, t[7] * 1e3);
         for (int i = 0; i < 8; ++i) cudaEventDestroy(dbg_ev[i]);
     }
+    return INF3DP_OK;
+}
+
+int64_t inf3dp_extract_isocontours_compact_rows(int nV, int nF, int K, size_t ws_bytes) {
+    (void)nV;
+    if (nF < 0 || K <= 0) return 0;
+    return 2ll * (int64_t)fit_capacity(nF, K, ws_bytes);
+}
+
+int inf3dp_extract_isocontours_compact(const float* V, const int32_t* F, const float* fields, const float* iso, int nV,
+                                       int nF, int K, float* rows, int64_t rows_capacity, int64_t* row_offsets,
+                                       int32_t* row_counts, int32_t* nums, void* ws, size_t ws_bytes,
+                                       inf3dp_stream_t stream) {
+    INF3DP_CHECK_ARG(nV >= 0 && nF >= 0 && K >= 0, "extract_isocontours_compact: negative size");
+    if (K == 0) return INF3DP_OK;
+    INF3DP_CHECK_ARG(iso && nums && ws && row_offsets && row_counts, "extract_isocontours_compact: null pointer");
+    INF3DP_CHECK_ARG(nF == 0 || (V && F && fields && rows), "extract_isocontours_compact: null pointer");
+    INF3DP_CHECK_ARG(K <= 12000, "extract_isocontours_compact: K=%d isovalues exceed the supported 12000", K);
+    INF3DP_CHECK_ARG((double)K * (double)nV * (double)nV < 9.0e18, "extract_isocontours_compact: K*nV^2 overflows the edge key");
+    ContourWs w = carve(ws, K, fit_capacity(nF, K, ws_bytes));
+    if (ws_bytes < w.total_bytes) {
+        set_error("extract_isocontours_compact: workspace has %zu bytes, need %zu", ws_bytes, w.total_bytes);
+        return INF3DP_EWORKSPACE;
+    }
+    INF3DP_CHECK_ARG(rows_capacity >= 2ll * w.cap, "extract_isocontours_compact: rows buffer holds %lld rows, need %lld "
+                     "(inf3dp_extract_isocontours_compact_rows)", (long long)rows_capacity, 2ll * w.cap);
+    w.compact = 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    contour_prep_kernel<<<1, 1024, 0, st>>>(iso, K, w);
+    INF3DP_LAUNCH_CHECK("contour_prep_kernel");
+    const int fblocks = (nF + kFaceThreads - 1) / kFaceThreads;
+    const size_t fsmem = (size_t)K * 8;
+    if (fblocks > 0) {
+        contour_faces_kernel<false><<<fblocks, kFaceThreads, fsmem, st>>>(V, F, fields, nV, nF, K, w);
+        INF3DP_LAUNCH_CHECK("contour_faces_kernel<count>");
+    }
+    contour_scan_kernel<<<1, 1024, 0, st>>>(K, w);
+    INF3DP_LAUNCH_CHECK("contour_scan_kernel");
+    if (nF > 0) {
+        const int sms = num_sms();
+        contour_hash_clear_kernel<<<sms * 4, 256, 0, st>>>(w);
+        INF3DP_LAUNCH_CHECK("contour_hash_clear_kernel");
+        contour_faces_kernel<true><<<fblocks, kFaceThreads, fsmem, st>>>(V, F, fields, nV, nF, K, w);
+        INF3DP_LAUNCH_CHECK("contour_faces_kernel<emit>");
+        contour_link_kernel<<<sms * 4, 256, 0, st>>>(w);
+        INF3DP_LAUNCH_CHECK("contour_link_kernel");
+    }
+    INF3DP_CUDA(cudaFuncSetAttribute(contour_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWalkSmemBytes));
+    contour_walk_kernel<<<K, kWalkThreads, kWalkSmemBytes, st>>>(nF, w, rows, nums);
+    INF3DP_LAUNCH_CHECK("contour_walk_kernel");
+    contour_export_kernel<<<(K + 255) / 256, 256, 0, st>>>(K, w, (long long*)row_offsets, row_counts);
+    INF3DP_LAUNCH_CHECK("contour_export_kernel");
     return INF3DP_OK;
 }
 

@@ -5,7 +5,8 @@ extraction, behind the reference's own Python surface.  See DESIGN.md and INTEGR
 """
 from . import _lib
 from .siren import SingleBVPNet, MLPClassifier, set_engine, get_engine
-from .contours import extract_isocontours, get_fields_intersection_inter_slice, extract_isocontours_raw
+from .contours import (extract_isocontours, get_fields_intersection_inter_slice, extract_isocontours_raw,
+                       extract_isocontours_compact, contour_loops)
 from .diffops import (gradient, hessian, hessian3d, jacobian, divergence, laplace, principal_curvatures,
                       min_max_curvs_and_vectors, unit_normals)
 from .query import field_querying, field_query_with_grads, HostPipeline
@@ -24,7 +25,8 @@ def patch_reference():
 
 __all__ = [
     "SingleBVPNet", "MLPClassifier", "set_engine", "get_engine", "extract_isocontours",
-    "get_fields_intersection_inter_slice", "extract_isocontours_raw", "gradient", "hessian", "hessian3d", "jacobian",
+    "get_fields_intersection_inter_slice", "extract_isocontours_raw", "extract_isocontours_compact", "contour_loops",
+    "gradient", "hessian", "hessian3d", "jacobian",
     "divergence", "laplace", "principal_curvatures", "min_max_curvs_and_vectors", "unit_normals", "field_querying",
     "field_query_with_grads", "HostPipeline", "patch_reference",
 ]

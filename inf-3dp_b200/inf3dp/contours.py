@@ -67,6 +67,66 @@ def extract_isocontours_raw(vertices, faces, fields, iso_values, sync=True, want
     return merged, nums
 
 
+def extract_isocontours_compact(vertices, faces, fields, iso_values):
+    """Compact row streams: -> rows [R,3] f32 (device), row_offsets [K] i64, row_counts [K] i32,
+    contour_nums [K] i32 (all on the device).  rows[row_offsets[k] : row_offsets[k] + row_counts[k]] is bit-identical to the
+    used prefix of extract_isocontours(...)[0][k]; the dense zero-padded [K,F,3] tensor is never produced."""
+    _check_input(vertices, "vertices", torch.float32)
+    _check_input(faces, "faces", torch.int32)
+    _check_input(fields, "fields", torch.float32)
+    _check_input(iso_values, "iso_values", torch.float32)
+    if vertices.dim() != 2 or vertices.shape[1] != 3 or faces.dim() != 2 or faces.shape[1] != 3:
+        raise RuntimeError("vertices must be [V,3] and faces [F,3]")
+    if fields.numel() != vertices.shape[0]:
+        raise RuntimeError("fields must hold one value per vertex")
+    dev = vertices.device
+    nV, nF, K = vertices.shape[0], faces.shape[0], iso_values.numel()
+    L = _lib.lib()
+    offs = torch.zeros((K,), dtype=torch.int64, device=dev)
+    counts = torch.zeros((K,), dtype=torch.int32, device=dev)
+    nums = torch.zeros((K,), dtype=torch.int32, device=dev)
+    if K == 0:
+        return torch.empty((0, 3), dtype=torch.float32, device=dev), offs, counts, nums
+    ws_bytes = L.inf3dp_extract_isocontours_workspace_bytes(nV, nF, K)
+    with torch.cuda.device(dev):
+        st = _lib.stream_ptr(dev)
+        for attempt in range(2):
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            cap_rows = L.inf3dp_extract_isocontours_compact_rows(nV, nF, K, ws_bytes)
+            rows = torch.empty((cap_rows, 3), dtype=torch.float32, device=dev)
+            _lib.check(L.inf3dp_extract_isocontours_compact(_lib.ptr(vertices), _lib.ptr(faces), _lib.ptr(fields),
+                                                            _lib.ptr(iso_values), nV, nF, K, _lib.ptr(rows), cap_rows,
+                                                            _lib.ptr(offs), _lib.ptr(counts), _lib.ptr(nums), _lib.ptr(ws),
+                                                            ws_bytes, st))
+            rc = L.inf3dp_extract_isocontours_status(_lib.ptr(ws), K, None, st)
+            if rc == _lib.EOVERFLOW and attempt == 0:
+                ws_bytes = L.inf3dp_extract_isocontours_workspace_bytes_segments(nV, nF, K, int(nF) * int(K))
+                continue
+            _lib.check(rc)
+            break
+    return rows, offs, counts, nums
+
+
+def contour_loops(vertices, faces, fields, iso_values):
+    """Per-isovalue list of closed / open polylines as host arrays -- what the reference obtains by copying the dense
+    [K,F,3] tensor to the host and scanning it for separator rows (toolpath_utils.py:38-82), here from one transfer of
+    the used rows only (tens of MB instead of 12*K*F bytes).  -> list over isovalues of lists of [n_i, 3] float32 arrays."""
+    rows, offs, counts, nums = extract_isocontours_compact(vertices, faces, fields, iso_values)
+    offs_h, counts_h = offs.cpu().numpy(), counts.cpu().numpy()
+    total = int((offs_h + counts_h).max()) if len(offs_h) else 0
+    rows_h = rows[:total].cpu().numpy()
+    out = []
+    for k in range(len(offs_h)):
+        r = rows_h[offs_h[k]: offs_h[k] + counts_h[k]]
+        sep = (r[:, 0] == -1e9).nonzero()[0] if len(r) else []
+        loops, start = [], 0
+        for e in sep:
+            loops.append(r[start:e])
+            start = e + 1
+        out.append(loops)
+    return out
+
+
 def extract_isocontours(vertices, faces, fields, iso_values):
     """qupkg.extract_isocontours.extract_isocontours -> [contours_merged, contour_nums] (isocontours.cu:292)."""
     merged, nums = extract_isocontours_raw(vertices, faces, fields, iso_values, sync=True)

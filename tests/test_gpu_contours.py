@@ -106,6 +106,33 @@ def test_randomly_torn_meshes_open_chains(nu, nv, K, drop, seed):
     assert_equivalent(m, n, s, mo, no, so_)
 
 
+@pytest.mark.parametrize("torn", [False, True])
+def test_compact_rows_equal_the_used_prefix_of_the_dense_contract(torn):
+    """extract_isocontours_compact / contour_loops: the compact row streams are bit-identical to the
+    used rows of the dense [K,F,3] result, and the host-side loops equal the reference's separator split."""
+    import inf3dp
+    V, F = co.torus_mesh(96, 48)
+    f = _field(V)
+    if torn:
+        rng = np.random.default_rng(5)
+        F = np.ascontiguousarray(F[rng.random(len(F)) >= 0.02])
+    iso = np.linspace(f.min(), f.max(), 31).astype(np.float32)
+    t = [torch.from_numpy(a).cuda() for a in (V, F, f, iso)]
+    m, n = inf3dp.extract_isocontours(*t)
+    rows, offs, counts, nums = inf3dp.extract_isocontours_compact(*t)
+    assert torch.equal(nums, n)
+    m, n = m.cpu().numpy(), n.cpu().numpy()
+    rows, offs, counts = rows.cpu().numpy(), offs.cpu().numpy(), counts.cpu().numpy()
+    for k in range(len(iso)):
+        used = co.rows_used(m[k], n[k])
+        assert counts[k] == used
+        assert np.array_equal(rows[offs[k]:offs[k] + used], m[k, :used])
+    loops = inf3dp.contour_loops(*t)
+    for k in range(len(iso)):
+        ref = co.split_rows(m[k], n[k])
+        assert len(loops[k]) == len(ref) and all(np.array_equal(a, b) for a, b in zip(loops[k], ref))
+
+
 def test_full_size_properties():
     """F = 0.5 M faces, K = 200: properties that hold at any size (no O(S^2) oracle here): rows used = S_k + C_k,
     zero padding, every long loop closes, determinism."""
