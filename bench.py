@@ -192,7 +192,9 @@ def bench_isocontours(dev, peaks):
             "config": {"workload": "200-isovalue isocontour extraction, closed torus mesh", "faces": nF,
                        "vertices": nV, "isovalues": K, "segments": S, "loops": C},
             "roofline": {"bound": "hbm", "achieved": contract / (ms / 1e3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
-                         "frac": contract / (ms / 1e3) / 1e9 / peaks["hbm"], "traffic": None,
+                         "frac": contract / (ms / 1e3) / 1e9 / peaks["hbm"],
+                         # dram bytes of the nine launches of one call (ncu --set full, profiles/r1b_isocontours_ncu_summary.md)
+                         "traffic": 2.46e9, "traffic_unit": "bytes per call (ncu)",
                          "bytes_contract": contract, "bytes_useful": useful,
                          "useful_gbs": useful / (ms / 1e3) / 1e9, "peak_source": peaks["source"]},
             "gpu_launches_per_call": 9}
@@ -230,6 +232,49 @@ def bench_hessian_sweep(net, dev, peaks):
             "ms_per_sweep": ms, "points": n, "kernel": "siren_rev_kernel<CTAS=2,KIND=1> (forward-mode second-order jet) + principal_curvatures_kernel",
             "flop_per_point": flop, "achieved_tflops": tf, "frac_of_sustained_peak": tf / peaks["tf_sustained"],
             "checksum": float(kap[:: n // 4096].double().sum())}
+
+
+def bench_collision(sdf_net, dev, n_waypoints=4_194_304, m_nozzle=64):
+    """BASELINE.json configs[3]: 4M-waypoint TV-SDF + quaternion-field collision query (SURVEY.md 8d cfg 4, M = 64 nozzle
+    points per waypoint): quaternion field -> posed nozzle clouds -> SDF value+gradient -> slice value+gradient on the
+    inside points -> level MLP -> predicates / Eq. 27 / two-step push (level_collision.py:73-237), device resident.
+    Synthetic fixtures: waypoints uniform on the torus surface (R 0.6, r 0.3), levels from 8 z-bands, nozzle = 64 points
+    of a 1/150-scaled cone shell, networks random-init (seed 2048 order); the SDF output bias is shifted by -0.06 so
+    that about half of the cube is inside the part (the raw random-init SDF is positive everywhere)."""
+    import copy
+    import math
+    import torch
+    import inf3dp
+    torch.manual_seed(2048)
+    nets = [inf3dp.SingleBVPNet(type="sine", in_features=3, out_features=o) for o in (1, 1, 1, 1, 4)]
+    slice_net, quat_net = nets[1].to(dev), nets[4].to(dev)
+    level = inf3dp.MLPClassifier(num_classes=8).to(dev)
+    sdf = copy.deepcopy(sdf_net)
+    with torch.no_grad():
+        sdf.net.net[4][0].bias -= 0.06
+    g = torch.Generator(device="cpu").manual_seed(4)
+    u = torch.rand(n_waypoints, generator=g) * 2 * math.pi
+    v = torch.rand(n_waypoints, generator=g) * 2 * math.pi
+    way = torch.stack([(0.6 + 0.3 * torch.cos(v)) * torch.cos(u), (0.6 + 0.3 * torch.cos(v)) * torch.sin(u), 0.3 * torch.sin(v)], 1).to(dev)
+    levels = ((way[:, 2] + 0.3) / 0.6 * 8).clamp(0, 7).long()
+    maxsl = (torch.rand((n_waypoints, 8), generator=g) * 0.1 - 0.05).to(dev)
+    t = torch.linspace(0, 1, m_nozzle)
+    nozzle = (torch.stack([0.5 * t * torch.cos(t * 40), 0.5 * t * torch.sin(t * 40), 0.2 + 4.0 * t], 1) / 150.0 * 20.0).to(dev)
+
+    def sweep():
+        return inf3dp.quat_collision_sweep(way, levels, maxsl, nozzle, quat_net, sdf, slice_net, level, 8, -0.9)
+    sweep()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    depth, hit = sweep()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1)
+    return {"metric": "collision_waypoints_per_s", "value": n_waypoints / (ms / 1e3), "unit": "waypoints/s", "ms_per_sweep": ms,
+            "waypoints": n_waypoints, "nozzle_points_per_waypoint": m_nozzle,
+            "nozzle_points_per_s": n_waypoints * m_nozzle / (ms / 1e3), "colliding_waypoints": int(hit.sum()),
+            "api": "inf3dp.quat_collision_sweep (quaternion field + level_collision.CollTVSDF forward, device resident)"}
 
 
 def run_ours(args):
@@ -340,6 +385,7 @@ def run_ours(args):
         peak = peaks["tf_sustained"]
         iso = bench_isocontours(dev, peaks)
         hess = bench_hessian_sweep(net, dev, peaks)
+        coll = bench_collision(net, dev)
         cores = os.cpu_count() or 1
         cpu_base = None
         if world == 1:   # reported baseline: rank 0 at N=1 only (torchrun pins OMP threads to 1 for N>1)
@@ -360,7 +406,11 @@ def run_ours(args):
                     "checksum": e2e_checksum},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": {"bound": "tensor", "achieved": kernel_tflops, "peak": peak, "unit": "TFLOP/s",
-                         "frac": kernel_tflops / peak, "traffic": None, "kernel": kernel_name,
+                         "frac": kernel_tflops / peak,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one bench-sized launch (ncu --set full,
+                         # profiles/r1b_siren_rev_ncu_summary.md); algorithmic HBM bytes are 28 per point = 3.76e9
+                         "traffic": 3.825e9 if engine == "tc_reverse" else None, "traffic_unit": "bytes per launch (ncu)",
+                         "kernel": kernel_name,
                          "kernel_ms": ms_kernel, "flop_per_point": flop_per_point,
                          "formulation": "reverse-mode (forward + backward sweep)" if engine == "tc_reverse" else "forward-mode jet",
                          "peak_kind": "bf16_tflops_sustained",
@@ -372,6 +422,7 @@ def run_ours(args):
             "cpu_baseline": cpu_base,
             "isocontour": iso,
             "hessian_sweep": hess,
+            "collision_sweep": coll,
             "clocks": clocks,
             "torch": torch.__version__,
         }

@@ -10,6 +10,9 @@ from .contours import (extract_isocontours, get_fields_intersection_inter_slice,
 from .diffops import (gradient, hessian, hessian3d, jacobian, divergence, laplace, principal_curvatures,
                       min_max_curvs_and_vectors, unit_normals)
 from .query import field_querying, field_query_with_grads, HostPipeline
+from .projection import batch_isosurface_projection, iter_project_contours_batch
+from .collision import (CollTVSDF, collision_evaluation, tvsdf_collision_forward, quat_collision_sweep,
+                        transform_nozzle_pcd_with_quaternion)
 
 
 def patch_reference():
@@ -28,5 +31,7 @@ __all__ = [
     "get_fields_intersection_inter_slice", "extract_isocontours_raw", "extract_isocontours_compact", "contour_loops",
     "gradient", "hessian", "hessian3d", "jacobian",
     "divergence", "laplace", "principal_curvatures", "min_max_curvs_and_vectors", "unit_normals", "field_querying",
-    "field_query_with_grads", "HostPipeline", "patch_reference",
+    "field_query_with_grads", "HostPipeline", "patch_reference", "batch_isosurface_projection",
+    "iter_project_contours_batch", "CollTVSDF", "collision_evaluation", "tvsdf_collision_forward", "quat_collision_sweep",
+    "transform_nozzle_pcd_with_quaternion",
 ]
