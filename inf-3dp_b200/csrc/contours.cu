@@ -53,6 +53,7 @@ struct ContourWs {
     int* hvals;          // [hcap][2]
     int cap;
     int hcap;
+    int defer;           // 1: the walk records the row order (endpoint ids) in seg_order, rows are written by the scatter kernel
     int compact;         // 1: rows of isovalue k go to merged + 6 * seg_offset[k] (at most 2 S_k rows), no dense contract
     size_t total_bytes;
 };
@@ -164,6 +165,9 @@ __device__ __forceinline__ float ld_keep(const float* a, unsigned long long pol)
 }
 __device__ __forceinline__ void st_keep(int* a, int v, unsigned long long pol) {
     asm volatile("st.global.L2::cache_hint.b32 [%0], %1, %2;" ::"l"(a), "r"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_keep(unsigned long long* a, unsigned long long v, unsigned long long pol) {
+    asm volatile("st.global.L2::cache_hint.b64 [%0], %1, %2;" ::"l"(a), "l"(v), "l"(pol) : "memory");
 }
 __device__ __forceinline__ void st_keep(float* a, float v, unsigned long long pol) {
     asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(a), "f"(v), "l"(pol) : "memory");
@@ -320,10 +324,11 @@ __global__ void contour_scan_kernel(int K, ContourWs w) {
 
 __global__ void contour_hash_clear_kernel(ContourWs w) {
     const int n = w.hdr[2];
+    const unsigned long long keep = keep_policy();   // the table is probed at random by `emit` and `link`: keep it in L2
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        w.hkeys[i] = kEmptyKey;
-        w.hvals[2 * i] = -1;
-        w.hvals[2 * i + 1] = -1;
+        st_keep(&w.hkeys[i], kEmptyKey, keep);
+        st_keep(&w.hvals[2 * i], -1, keep);
+        st_keep(&w.hvals[2 * i + 1], -1, keep);
     }
 }
 
@@ -334,7 +339,7 @@ __global__ void contour_link_kernel(ContourWs w) {
     const unsigned long long keep = keep_policy();
     for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < n; id += gridDim.x * blockDim.x) {
         const int hs = ld_keep(&w.seg_slot[id], keep);
-        const int a = w.hvals[2 * hs], b = w.hvals[2 * hs + 1];
+        const int a = ld_keep(&w.hvals[2 * hs], keep), b = ld_keep(&w.hvals[2 * hs + 1], keep);
         int partner = (a == id) ? b : (b == id ? a : -1);
         if (partner >= 0) {
             const float* p = w.seg_pts + 3ll * id;  // [seg][side][3] == flat [id][3]
@@ -490,8 +495,14 @@ __device__ __forceinline__ void walk_isovalue(int S, int off, int nF, int k, con
         w.rows_used[k] = min(row, limit);
     }
     __syncthreads();
-    // phase 2: all threads gather the points and write the row stream
+    // phase 2: all threads gather the points and write the row stream (or hand the row order to the scatter kernel)
     const int rows = min(s_rows, limit);
+    if (w.defer) {
+        int* gorder = w.seg_order + 2ll * off;
+        if ((const void*)gorder != (const void*)order)
+            for (int r = threadIdx.x; r < rows; r += blockDim.x) { const IdxT e = order[r]; gorder[r] = X::is_point(e) ? (int)e : -2; }
+        return;
+    }
     for (int r = threadIdx.x; r < rows; r += blockDim.x) {
         const IdxT e = order[r];
         float a = -1e9f, b = -1e9f, c = -1e9f;
@@ -778,13 +789,16 @@ __device__ bool walk_ranked(int S, int off, int nF, int k, const ContourWs& w, u
     const float* pts = w.seg_pts + 6ll * off;
     int limit;
     float* out = row_window(w, k, off, S, nF, merged, limit);
+    int* gorder = w.seg_order + 2ll * off;
     auto emit_row = [&](int row, int endpoint) {
+        if (w.defer) { if (row < limit) gorder[row] = endpoint; return; }
         if (row < limit) {
             const float* q = pts + 3ll * endpoint;
             out[3ll * row] = ld_keep(q, keep); out[3ll * row + 1] = ld_keep(q + 1, keep); out[3ll * row + 2] = ld_keep(q + 2, keep);
         }
     };
     auto emit_separator = [&](int row) {
+        if (w.defer) { if (row < limit) gorder[row] = -2; return; }
         if (row < limit) { float* sp = out + 3ll * row; sp[0] = -1e9f; sp[1] = -1e9f; sp[2] = -1e9f; }
     };
     for (int e = tid; e < n; e += kWalkThreads) {
@@ -903,6 +917,45 @@ int get_side_stream(cudaStream_t* out) {
 }
 
 // Largest pool that fits the caller's workspace (>= the default, doubling).
+// Zero fill of the whole dense contract (12 K F bytes), independent of every other kernel of the call: it starts at t = 0
+// on the caller's stream while the chain runs on the helper stream.  Many short blocks (see contour_fill_kernel).
+__global__ void __launch_bounds__(256)
+contour_fill_all_kernel(float* __restrict__ merged, long long nfloat) {
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nth = (long long)gridDim.x * blockDim.x;
+    const uintptr_t addr0 = reinterpret_cast<uintptr_t>(merged);
+    long long head = ((16 - (addr0 & 15)) & 15) >> 2;
+    if (head > nfloat) head = nfloat;
+    const long long nvec = (nfloat - head) >> 2;
+    const long long tail0 = head + 4 * nvec;
+    if (tid < head) merged[tid] = 0.f;
+    if (tid < nfloat - tail0) merged[tail0 + tid] = 0.f;
+    float4* vb = reinterpret_cast<float4*>(merged + head);
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (long long i = tid; i < nvec; i += nth) __stcs(vb + i, z);
+}
+
+// Rows of the dense contract from the recorded row order (after the fill): out[k][r] = point of endpoint order[r], or the
+// (-1e9) separator.
+__global__ void __launch_bounds__(256)
+contour_scatter_kernel(int nF, int K, ContourWs w, float* __restrict__ merged) {
+    const unsigned long long keep = keep_policy();
+    for (int k = blockIdx.y; k < K; k += gridDim.y) {
+        const int rows = w.hdr[0] != 0 ? 0 : w.rows_used[k];
+        const int off = w.seg_offset[k];
+        const int* order = w.seg_order + 2ll * off;
+        const float* pts = w.seg_pts + 6ll * off;
+        float* out = merged + (size_t)k * nF * 3;
+        for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += gridDim.x * blockDim.x) {
+            const int e = ld_keep(order + r, keep);
+            float a = -1e9f, b = -1e9f, c = -1e9f;
+            if (e >= 0) { const float* q = pts + 3ll * e; a = ld_keep(q, keep); b = ld_keep(q + 1, keep); c = ld_keep(q + 2, keep); }
+            out[3ll * r] = a; out[3ll * r + 1] = b; out[3ll * r + 2] = c;
+        }
+    }
+}
+
 // compact layout bookkeeping for the caller: row offset / row count of every isovalue
 __global__ void contour_export_kernel(int K, ContourWs w, long long* __restrict__ row_offsets, int* __restrict__ row_counts) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -973,59 +1026,61 @@ int inf3dp_extract_isocontours(const float* V, const int32_t* F, const float* fi
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     INF3DP_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
     INF3DP_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    w.defer = 1;
 
-    contour_prep_kernel<<<1, 1024, 0, st>>>(iso, K, w);
-    INF3DP_LAUNCH_CHECK("contour_prep_kernel");
-    const int fblocks = (nF + kFaceThreads - 1) / kFaceThreads;
-    const size_t fsmem = (size_t)K * 8;
-    if (fblocks > 0) {
-        contour_faces_kernel<false><<<fblocks, kFaceThreads, fsmem, st>>>(V, F, fields, nV, nF, K, w);
-        INF3DP_LAUNCH_CHECK("contour_faces_kernel<count>");
-    }
-    contour_scan_kernel<<<1, 1024, 0, st>>>(K, w);
-    INF3DP_LAUNCH_CHECK("contour_scan_kernel");
-
-    // fork: the chain (hash/link/walk) goes to the high-priority helper stream, the bulk zero fill stays on the
-    // caller's stream; join before the tail fill (which needs the row counts the walk produced)
+    // fork at t = 0.  Helper stream (highest priority): the whole latency-bound chain prep -> count -> scan -> hash
+    // clear -> emit -> link -> walk, which only RECORDS the row order of every isovalue.  Caller's stream: the zero fill
+    // of the dense contract, which depends on nothing.  Join, then the recorded rows are scattered over the zeros.
     INF3DP_CUDA(cudaEventRecord(ev_fork, st));
     mark(1, st);
     INF3DP_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
-    if (nF > 0 && dev_skip != 2) {
-        contour_hash_clear_kernel<<<sms * 4, 256, 0, side>>>(w);
-        INF3DP_LAUNCH_CHECK("contour_hash_clear_kernel");
-        contour_faces_kernel<true><<<fblocks, kFaceThreads, fsmem, side>>>(V, F, fields, nV, nF, K, w);
-        INF3DP_LAUNCH_CHECK("contour_faces_kernel<emit>");
-        mark(4, side);
-        contour_link_kernel<<<sms * 4, 256, 0, side>>>(w);
-        INF3DP_LAUNCH_CHECK("contour_link_kernel");
-        mark(5, side);
-    }
-    INF3DP_CUDA(cudaFuncSetAttribute(contour_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     kWalkSmemBytes));
-    if (dev_skip != 2) contour_walk_kernel<<<K, kWalkThreads, kWalkSmemBytes, side>>>(nF, w, merged, nums);
-    INF3DP_LAUNCH_CHECK("contour_walk_kernel");
-    INF3DP_CUDA(cudaEventRecord(ev_join, side));
-    mark(6, side);
-
+    // (the fill is enqueued first: seven chain launches cost ~30 us of host time that it would otherwise wait for)
     mark(2, st);
     if (nF > 0 && dev_skip != 1) {
         // Many SHORT blocks (each thread streams ~16 float4 stores): SM slots free up continuously, so the
-        // higher-priority chain kernels on the helper stream are dispatched between them.  (Measured alternatives:
+        // higher-priority chain kernels on the helper stream are dispatched between them.  (Measured alternative:
         // a persistent 2-CTA/SM fill cannot keep enough stores in flight -- 3.8 TB/s instead of 6.1 TB/s.)
-        const long long per_iso_vec = (3ll * nF) / 4 + 1;
-        long long gxl = per_iso_vec / 4096;
-        if (gxl < 1) gxl = 1;
-        if (gxl > 256) gxl = 256;
-        dim3 grid((int)gxl, K);
-        contour_fill_kernel<0><<<grid, 256, 0, st>>>(nF, K, w, merged);
-        INF3DP_LAUNCH_CHECK("contour_fill_kernel<0>");
+        const long long nfloat = 3ll * (long long)nF * (long long)K;
+        long long blocks = (nfloat / 4 + 4095) / 4096;
+        if (blocks < 1) blocks = 1;
+        if (blocks > 65535ll * 16) blocks = 65535ll * 16;
+        contour_fill_all_kernel<<<(unsigned)blocks, 256, 0, st>>>(merged, nfloat);
+        INF3DP_LAUNCH_CHECK("contour_fill_all_kernel");
     }
+    const int fblocks = (nF + kFaceThreads - 1) / kFaceThreads;
+    const size_t fsmem = (size_t)K * 8;
+    if (dev_skip != 2) {
+        contour_prep_kernel<<<1, 1024, 0, side>>>(iso, K, w);
+        INF3DP_LAUNCH_CHECK("contour_prep_kernel");
+        if (fblocks > 0) {
+            contour_faces_kernel<false><<<fblocks, kFaceThreads, fsmem, side>>>(V, F, fields, nV, nF, K, w);
+            INF3DP_LAUNCH_CHECK("contour_faces_kernel<count>");
+        }
+        contour_scan_kernel<<<1, 1024, 0, side>>>(K, w);
+        INF3DP_LAUNCH_CHECK("contour_scan_kernel");
+        if (nF > 0) {
+            contour_hash_clear_kernel<<<sms * 4, 256, 0, side>>>(w);
+            INF3DP_LAUNCH_CHECK("contour_hash_clear_kernel");
+            contour_faces_kernel<true><<<fblocks, kFaceThreads, fsmem, side>>>(V, F, fields, nV, nF, K, w);
+            INF3DP_LAUNCH_CHECK("contour_faces_kernel<emit>");
+            mark(4, side);
+            contour_link_kernel<<<sms * 4, 256, 0, side>>>(w);
+            INF3DP_LAUNCH_CHECK("contour_link_kernel");
+            mark(5, side);
+        }
+        INF3DP_CUDA(cudaFuncSetAttribute(contour_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWalkSmemBytes));
+        contour_walk_kernel<<<K, kWalkThreads, kWalkSmemBytes, side>>>(nF, w, merged, nums);
+        INF3DP_LAUNCH_CHECK("contour_walk_kernel");
+    }
+    INF3DP_CUDA(cudaEventRecord(ev_join, side));
+    mark(6, side);
+
     mark(3, st);
     INF3DP_CUDA(cudaStreamWaitEvent(st, ev_join, 0));  // join
-    if (nF > 0) {
+    if (nF > 0 && dev_skip != 2) {
         dim3 grid(8, K);
-        contour_fill_kernel<1><<<grid, 256, 0, st>>>(nF, K, w, merged);
-        INF3DP_LAUNCH_CHECK("contour_fill_kernel<1>");
+        contour_scatter_kernel<<<grid, 256, 0, st>>>(nF, K, w, merged);
+        INF3DP_LAUNCH_CHECK("contour_scatter_kernel");
     }
     mark(7, st);
     INF3DP_CUDA(cudaEventDestroy(ev_fork));
@@ -1047,7 +1102,7 @@ int inf3dp_extract_isocontours(const float* V, const int32_t* F, const float* fi
                     (double)sum / (K > 0 ? K : 1), cyc[kmax], kmax, cnt[kmax], smax);
         }
         fprintf(stderr, "[inf3dp contour debug] us since start: fork %.0f | caller stream: fill start %.0f end %.0f | chain stream: emit end %.0f "
-                        "link end %.0f walk end %.0f | tail fill end %.0f\n", t[1] * 1e3, t[2] * 1e3, t[3] * 1e3, t[4] * 1e3,
+                        "link end %.0f walk end %.0f | scatter end %.0f\n", t[1] * 1e3, t[2] * 1e3, t[3] * 1e3, t[4] * 1e3,
                 t[5] * 1e3, t[6] * 1e3, t[7] * 1e3);
         for (int i = 0; i < 8; ++i) cudaEventDestroy(dbg_ev[i]);
     }
