@@ -12,6 +12,8 @@
 //     elects the LOWEST linear voxel index per cell with atomicMin and pass 2 -- run only over the compacted
 //     list of voxels that hit anything -- lets the winner write.  Deterministic, one full read of the fields.
 //   * outputs are initialised by the same call (mask 0, indices -1, points 0), 16-byte vectorised
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace inf3dp {
@@ -75,31 +77,13 @@ __global__ void isect_prep_kernel(const float* s_iso, const float* a_iso, const 
     rank_sort(b_iso, N2, w.iso_sorted[2], w.iso_perm[2], &w.hdr[6]);
 }
 
-// Output + winner initialisation, flat over cells (4 cells per thread so every store is 4..16 bytes wide).
-__global__ void isect_init_kernel(long long cells, int* __restrict__ winner, uint8_t* __restrict__ mask,
-                                  int16_t* __restrict__ idx, float* __restrict__ pts) {
+// Winner initialisation (the outputs are initialised by the cell kernel).
+__global__ void isect_init_kernel(long long cells, int* __restrict__ winner) {
     const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // quad of cells
     const long long c0 = q * 4;
     if (c0 >= cells) return;
-    if (c0 + 4 <= cells) {
-        // torch allocations are >= 256-byte aligned, so these vector stores are aligned for any quad index
-        *reinterpret_cast<int4*>(winner + c0) = make_int4(0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff);
-        *reinterpret_cast<uint32_t*>(mask + c0) = 0u;
-        uint2* ip = reinterpret_cast<uint2*>(idx + 3 * c0);  // 12 int16 = 24 bytes
-        ip[0] = make_uint2(0xffffffffu, 0xffffffffu);
-        ip[1] = make_uint2(0xffffffffu, 0xffffffffu);
-        ip[2] = make_uint2(0xffffffffu, 0xffffffffu);
-        float4* pp = reinterpret_cast<float4*>(pts + 3 * c0);  // 12 floats = 48 bytes
-        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        pp[0] = z; pp[1] = z; pp[2] = z;
-    } else {
-        for (long long c = c0; c < cells; ++c) {
-            winner[c] = 0x7fffffff;
-            mask[c] = 0;
-            idx[3 * c] = -1; idx[3 * c + 1] = -1; idx[3 * c + 2] = -1;
-            pts[3 * c] = 0.f; pts[3 * c + 1] = 0.f; pts[3 * c + 2] = 0.f;
-        }
-    }
+    if (c0 + 4 <= cells) *reinterpret_cast<int4*>(winner + c0) = make_int4(0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff);
+    else for (long long c = c0; c < cells; ++c) winner[c] = 0x7fffffff;
 }
 
 // intersection.cu:8-27 -- note that corner 0 is never NaN-tested by the reference; a NaN there leaves
@@ -127,6 +111,36 @@ __device__ __forceinline__ void iso_window(const float* __restrict__ sorted, int
     hi = a;
 }
 
+// The three sorted isovalue arrays and their permutations, staged in shared memory per block (a voxel makes ~25
+// dependent probes into them; from global memory those probes were the elect kernel's critical path).
+struct IsoTables {
+    const float* sorted[3];
+    const int* perm[3];
+    int n[3];   // finite isovalues only
+};
+constexpr int kMaxTableEntries = 6000;   // 48 KB of shared memory; larger isovalue sets are probed in global memory
+
+__device__ __forceinline__ IsoTables load_tables(const IsectWs& w, unsigned char* smem, int Ns, int N1, int N2) {
+    IsoTables t;
+    const int full[3] = {Ns, N1, N2};
+    t.n[0] = w.hdr[4]; t.n[1] = w.hdr[5]; t.n[2] = w.hdr[6];
+    if (Ns + N1 + N2 > kMaxTableEntries) {
+        for (int i = 0; i < 3; ++i) { t.sorted[i] = w.iso_sorted[i]; t.perm[i] = w.iso_perm[i]; }
+        return t;
+    }
+    float* fs = reinterpret_cast<float*>(smem);
+    int* ps = reinterpret_cast<int*>(fs + (Ns + N1 + N2));
+    int o = 0;
+    for (int i = 0; i < 3; ++i) {
+        for (int j = threadIdx.x; j < full[i]; j += blockDim.x) { fs[o + j] = w.iso_sorted[i][j]; ps[o + j] = w.iso_perm[i][j]; }
+        t.sorted[i] = fs + o;
+        t.perm[i] = ps + o;
+        o += full[i];
+    }
+    __syncthreads();
+    return t;
+}
+
 struct VoxelFields {
     float4 s[2], a[2], b[2];
 };
@@ -146,19 +160,19 @@ struct Windows {
     bool any;
 };
 
-__device__ __forceinline__ Windows voxel_windows(const VoxelFields& f, const IsectWs& w, int, int, int) {
-    const int Ns = w.hdr[4], N1 = w.hdr[5], N2 = w.hdr[6];  // finite isovalues only
+__device__ __forceinline__ Windows voxel_windows(const VoxelFields& f, const IsoTables& w) {
+    const int Ns = w.n[0], N1 = w.n[1], N2 = w.n[2];  // finite isovalues only
     Windows r{};
     r.any = false;
     float amn, amx, bmn, bmx, smn, smx;
     if (!min_max8(f.a[0], f.a[1], amn, amx)) return r;  // order of intersection.cu:79-91
     if (!min_max8(f.b[0], f.b[1], bmn, bmx)) return r;
     if (!min_max8(f.s[0], f.s[1], smn, smx)) return r;
-    iso_window(w.iso_sorted[1], N1, amn, amx, r.a0, r.a1);
+    iso_window(w.sorted[1], N1, amn, amx, r.a0, r.a1);
     if (r.a0 >= r.a1) return r;
-    iso_window(w.iso_sorted[2], N2, bmn, bmx, r.b0, r.b1);
+    iso_window(w.sorted[2], N2, bmn, bmx, r.b0, r.b1);
     if (r.b0 >= r.b1) return r;
-    iso_window(w.iso_sorted[0], Ns, smn, smx, r.s0, r.s1);
+    iso_window(w.sorted[0], Ns, smn, smx, r.s0, r.s1);
     if (r.s0 >= r.s1) return r;
     r.any = true;
     return r;
@@ -168,35 +182,34 @@ __device__ __forceinline__ Windows voxel_windows(const VoxelFields& f, const Ise
 __global__ void __launch_bounds__(256)
 isect_elect_kernel(const float* __restrict__ sf, const float* __restrict__ af, const float* __restrict__ bf,
                    long long voxels, int Ns, int N1, int N2, IsectWs w) {
-    const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    extern __shared__ unsigned char s_tab[];
+    const IsoTables tb = load_tables(w, s_tab, Ns, N1, N2);
+    // persistent blocks: the tables are staged once per block, voxels are visited in block-sized strides
+    for (long long base = (long long)blockIdx.x * blockDim.x; base < voxels; base += (long long)gridDim.x * blockDim.x) {
+    const long long v = base + threadIdx.x;
     bool hit = false;
     if (v < voxels) {
         VoxelFields f;
         load_voxel(sf, af, bf, v, f);
-        const Windows r = voxel_windows(f, w, Ns, N1, N2);
+        const Windows r = voxel_windows(f, tb);
         if (r.any) {
             hit = true;
             for (int ja = r.a0; ja < r.a1; ++ja) {
-                const int i1 = w.iso_perm[1][ja];
+                const int i1 = tb.perm[1][ja];
                 for (int jb = r.b0; jb < r.b1; ++jb) {
-                    const int i2 = w.iso_perm[2][jb];
+                    const int i2 = tb.perm[2][jb];
                     for (int js = r.s0; js < r.s1; ++js) {
-                        const int is = w.iso_perm[0][js];
+                        const int is = tb.perm[0][js];
                         const long long c = ((long long)is * N1 + i1) * N2 + i2;
-                        atomicMin(&w.winner[c], (int)v);
+                        // voxels are visited in roughly ascending order and ~3 of them hit every cell: most of the time
+                        // the cell already holds a smaller index, and a plain load is much cheaper than an L2 atomic
+                        if (__ldcg(&w.winner[c]) > (int)v) atomicMin(&w.winner[c], (int)v);
                     }
                 }
             }
         }
     }
-    // warp-aggregated append to the work list
-    const unsigned m = __ballot_sync(0xffffffffu, hit);
-    if (m) {
-        const int lane = threadIdx.x & 31;
-        int base = 0;
-        if (lane == __ffs(m) - 1) base = atomicAdd(&w.hdr[0], __popc(m));
-        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-        if (hit) w.worklist[base + __popc(m & ((1u << lane) - 1u))] = (int)v;
+    (void)hit;
     }
 }
 
@@ -230,48 +243,59 @@ __device__ __forceinline__ int edge_sum(const float4 lo, const float4 hi, float 
     return cnt;
 }
 
-// pass 2: winners write their cells.  One thread per work-list voxel.
+// pass 2, cell centric: one thread per cell.  A cell without a winner gets the "nothing here" outputs (mask 0,
+// indices -1, point 0: no separate initialisation pass); otherwise the cell's winner voxel is re-read (96 B of corner
+// fields + its centre) and the three edge sums are evaluated for exactly this cell's isovalues.  Uniform work per
+// thread, no index windows.  A block covers 8 consecutive slice isovalues x 32 consecutive lattice-2 isovalues of one
+// lattice-1 isovalue: every warp writes 32 consecutive cells (coalesced rows), and the 8 warps mostly re-read the SAME
+// winner voxels (a voxel typically spans 2-3 neighbouring slice isovalues), which the L1 serves.
+constexpr int kCellTileS = 8, kCellTile2 = 32;
+
 __global__ void __launch_bounds__(256)
-isect_write_kernel(const float* __restrict__ sf, const float* __restrict__ af, const float* __restrict__ bf,
-                   const float* __restrict__ centers, int Dx, int Ns, int N1, int N2, IsectWs w,
-                   uint8_t* __restrict__ mask, int16_t* __restrict__ idx, float* __restrict__ pts) {
-    const int nwork = w.hdr[0];
+isect_cell_kernel(const float* __restrict__ sf, const float* __restrict__ af, const float* __restrict__ bf,
+                  const float* __restrict__ centers, const float* __restrict__ s_iso, const float* __restrict__ a_iso,
+                  const float* __restrict__ b_iso, int Dx, int Ns, int N1, int N2, long long tiles, IsectWs w,
+                  uint8_t* __restrict__ mask, int16_t* __restrict__ idx, float* __restrict__ pts) {
     const float vs = (float)(2.0 / (double)(float)Dx);  // intersection.cu:54
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nwork; i += gridDim.x * blockDim.x) {
-        const long long v = w.worklist[i];
+    const int tiles2 = (N2 + kCellTile2 - 1) / kCellTile2;
+    const int r = threadIdx.x >> 5, q = threadIdx.x & 31;
+    for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const int t2 = (int)(t % tiles2);
+        const long long u = t / tiles2;
+        const int i1 = (int)(u % N1);
+        const int ts = (int)(u / N1);
+        const int is = ts * kCellTileS + r, i2 = t2 * kCellTile2 + q;
+        if (is >= Ns || i2 >= N2) continue;
+        const long long c = ((long long)is * N1 + i1) * N2 + i2;
+        const int v = __ldcs(&w.winner[c]);
+        if (v == 0x7fffffff) {
+            mask[c] = 0;
+            idx[3 * c] = -1; idx[3 * c + 1] = -1; idx[3 * c + 2] = -1;
+            pts[3 * c] = 0.f; pts[3 * c + 1] = 0.f; pts[3 * c + 2] = 0.f;
+            continue;
+        }
         VoxelFields f;
-        load_voxel(sf, af, bf, v, f);
-        const Windows r = voxel_windows(f, w, Ns, N1, N2);
-        if (!r.any) continue;
-        const float ctr[3] = {centers[3 * v], centers[3 * v + 1], centers[3 * v + 2]};
-        for (int ja = r.a0; ja < r.a1; ++ja) {
-            const int i1 = w.iso_perm[1][ja];
-            const float aiso = w.iso_sorted[1][ja];
-            float pa[3];
-            const int ca = edge_sum(f.a[0], f.a[1], aiso, ctr, vs, pa);
-            for (int jb = r.b0; jb < r.b1; ++jb) {
-                const int i2 = w.iso_perm[2][jb];
-                const float biso = w.iso_sorted[2][jb];
-                float pb[3];
-                const int cb = edge_sum(f.b[0], f.b[1], biso, ctr, vs, pb);
-                for (int js = r.s0; js < r.s1; ++js) {
-                    const int is = w.iso_perm[0][js];
-                    const long long c = ((long long)is * N1 + i1) * N2 + i2;
-                    if (w.winner[c] != (int)v) continue;
-                    const float siso = w.iso_sorted[0][js];
-                    float ps[3];
-                    const int cs = edge_sum(f.s[0], f.s[1], siso, ctr, vs, ps);
-                    idx[3 * c] = (int16_t)is; idx[3 * c + 1] = (int16_t)i1; idx[3 * c + 2] = (int16_t)i2;
-                    mask[c] = 1;
+        {
+            const float4* sp = reinterpret_cast<const float4*>(sf) + 2ll * v;
+            const float4* ap = reinterpret_cast<const float4*>(af) + 2ll * v;
+            const float4* bp = reinterpret_cast<const float4*>(bf) + 2ll * v;
+            f.s[0] = __ldg(sp); f.s[1] = __ldg(sp + 1);
+            f.a[0] = __ldg(ap); f.a[1] = __ldg(ap + 1);
+            f.b[0] = __ldg(bp); f.b[1] = __ldg(bp + 1);
+        }
+        const float ctr[3] = {__ldg(centers + 3ll * v), __ldg(centers + 3ll * v + 1), __ldg(centers + 3ll * v + 2)};
+        float pa[3], pb[3], ps[3];
+        const int ca = edge_sum(f.a[0], f.a[1], a_iso[i1], ctr, vs, pa);
+        const int cb = edge_sum(f.b[0], f.b[1], b_iso[i2], ctr, vs, pb);
+        const int cs = edge_sum(f.s[0], f.s[1], s_iso[is], ctr, vs, ps);
+        idx[3 * c] = (int16_t)is; idx[3 * c + 1] = (int16_t)i1; idx[3 * c + 2] = (int16_t)i2;
+        mask[c] = 1;
 #pragma unroll
-                    for (int d = 0; d < 3; ++d) {  // intersection.cu:203-213
-                        const float xs = cs > 0 ? __fdiv_rn(ps[d], (float)cs) : ps[d];
-                        const float xa = ca > 0 ? __fdiv_rn(pa[d], (float)ca) : pa[d];
-                        const float xb = cb > 0 ? __fdiv_rn(pb[d], (float)cb) : pb[d];
-                        pts[3 * c + d] = (float)((double)(xs + xa + xb) / 3.0);
-                    }
-                }
-            }
+        for (int d = 0; d < 3; ++d) {  // intersection.cu:203-213
+            const float xs = cs > 0 ? __fdiv_rn(ps[d], (float)cs) : ps[d];
+            const float xa = ca > 0 ? __fdiv_rn(pa[d], (float)ca) : pa[d];
+            const float xb = cb > 0 ? __fdiv_rn(pb[d], (float)cb) : pb[d];
+            pts[3 * c + d] = (float)((double)(xs + xa + xb) / 3.0);
         }
     }
 }
@@ -314,13 +338,21 @@ int inf3dp_fields_intersection(const float* sf, const float* af, const float* bf
     isect_prep_kernel<<<1, 1024, 0, st>>>(s_iso, a_iso, b_iso, Ns, N1, N2, w);
     INF3DP_LAUNCH_CHECK("isect_prep_kernel");
     const long long quads = (cells + 3) / 4;
-    isect_init_kernel<<<(unsigned)((quads + 255) / 256), 256, 0, st>>>(cells, w.winner, mask, idx, pts);
+    isect_init_kernel<<<(unsigned)((quads + 255) / 256), 256, 0, st>>>(cells, w.winner);
     INF3DP_LAUNCH_CHECK("isect_init_kernel");
     if (voxels > 0) {
-        isect_elect_kernel<<<(unsigned)((voxels + 255) / 256), 256, 0, st>>>(sf, af, bf, voxels, Ns, N1, N2, w);
+        const size_t tab_smem = (Ns + N1 + N2) <= kMaxTableEntries ? (size_t)(Ns + N1 + N2) * 8 : 0;
+        if (tab_smem > 40 * 1024) {
+            INF3DP_CUDA(cudaFuncSetAttribute(isect_elect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tab_smem));
+        }
+        isect_elect_kernel<<<(unsigned)std::min<long long>((voxels + 255) / 256, (long long)num_sms() * 16), 256, tab_smem, st>>>(sf, af, bf, voxels, Ns, N1, N2, w);
         INF3DP_LAUNCH_CHECK("isect_elect_kernel");
-        isect_write_kernel<<<num_sms() * 8, 256, 0, st>>>(sf, af, bf, centers, Dx, Ns, N1, N2, w, mask, idx, pts);
-        INF3DP_LAUNCH_CHECK("isect_write_kernel");
+    }
+    {   // cells without a winner (all of them when there are no voxels) get the default outputs here
+        const long long tiles = (long long)((Ns + kCellTileS - 1) / kCellTileS) * N1 * ((N2 + kCellTile2 - 1) / kCellTile2);
+        const long long blocks = std::min<long long>(tiles, (long long)num_sms() * 32);
+        isect_cell_kernel<<<(unsigned)blocks, 256, 0, st>>>(sf, af, bf, centers, s_iso, a_iso, b_iso, Dx, Ns, N1, N2, tiles, w, mask, idx, pts);
+        INF3DP_LAUNCH_CHECK("isect_cell_kernel");
     }
     return INF3DP_OK;
 }
