@@ -186,7 +186,7 @@ int inf3dp_siren_pack_weights(const float* const* W, const float* const* b, int 
     h.off_wout = lay.off_wout; h.off_bout = lay.off_bout; h.off_tc = lay.tc_ok ? lay.off_tc : 0;
     h.total_bytes = lay.total;
     h.tc_scale = 1.f; h.tc_inv_scale = 1.f;
-    h.off_rev = lay.rev_ok ? lay.off_rev : 0; h.rev_ok = 0;
+    h.off_rev = (lay.rev_ok || lay.mlp_ok) ? lay.off_rev : 0; h.rev_ok = 0; h.mlp_ok = 0;
 
     pack_first_layer<<<(hidden + 255) / 256, 256, 0, st>>>(W[0], b[0], in_features, hidden, scale,
                                                           (float*)(base + lay.off_w0), (float*)(base + lay.off_b0));
@@ -208,6 +208,10 @@ int inf3dp_siren_pack_weights(const float* const* W, const float* const* b, int 
             rc = siren_rev_pack(W, omega0, siren_tc_maxabs_bits(packed, lay), packed, lay, h, st);
             if (rc != INF3DP_OK) return rc;
         }
+    }
+    if (lay.mlp_ok) {
+        int rc = siren_mlp_pack(W, b, out_features, packed, lay, h, st);
+        if (rc != INF3DP_OK) return rc;
     }
     INF3DP_CUDA(cudaMemcpyAsync(packed, &h, sizeof(h), cudaMemcpyHostToDevice, st));
     // the header copy reads a stack object: make sure it has left the host before returning
@@ -236,17 +240,20 @@ int inf3dp_siren_jet_ws(const void* packed, const float* x, int64_t n, int order
     const bool tc_capable = h.tc_ok && order <= 1;
     const bool rev_capable = h.rev_ok && order == 1;
     const bool jet2_capable = h.rev_ok && order == 2;   // single-output sine network: Hessian on the tensor cores
+    const bool mlp_capable = h.mlp_ok && order == 0;    // ReLU level classifier on the tensor cores
     const bool have_ws = workspace != nullptr && workspace_bytes >= siren_rev_workspace_bytes();
     switch (mode) {
         case INF3DP_MODE_AUTO:
             if (rev_capable && have_ws) return siren_rev_launch(packed, h, x, n, y, J, workspace, workspace_bytes, st);
             if (jet2_capable) return siren_jet2_launch(packed, h, x, n, y, J, H, st);
+            if (mlp_capable) return siren_mlp_launch(packed, h, x, n, y, st);
             if (tc_capable) return siren_tc_launch(packed, h, x, n, order, y, J, true, st);
             return siren_simt_launch(packed, h, x, n, order, y, J, H, st);
         case INF3DP_MODE_SIMT:
             return siren_simt_launch(packed, h, x, n, order, y, J, H, st);
         case INF3DP_MODE_TC_PRECISE:
             if (jet2_capable) return siren_jet2_launch(packed, h, x, n, y, J, H, st);
+            if (mlp_capable) return siren_mlp_launch(packed, h, x, n, y, st);
             /* fallthrough */
         case INF3DP_MODE_TC_FAST:
             INF3DP_CHECK_ARG(tc_capable, "siren_jet: tensor-core engine needs sine, in=3, hidden=256, 3 hidden layers, "

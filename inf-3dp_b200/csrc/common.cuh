@@ -78,18 +78,20 @@ struct SirenHeader {
     float tc_inv_scale;
     uint64_t off_rev;      // reverse-mode tcgen05 operand images (see siren_rev.cu), 0 if !rev_ok
     int rev_ok;            // flagship configuration with out_features == 1: the reverse-mode engine may be used
-    uint32_t pad[25];
+    int mlp_ok;            // ReLU classifier 4 -> 256 -> 256 -> C (C <= 16): off_rev holds its CTA-pair operand image
+    uint32_t pad[24];
 };
 static_assert(sizeof(SirenHeader) <= 256, "header must fit 256 bytes");
 
 struct SirenLayout {
     size_t off_w0, off_b0, off_wt, off_b, off_wout, off_bout, off_tc, off_rev, total;
-    bool tc_ok, rev_ok;
+    bool tc_ok, rev_ok, mlp_ok;
 };
 
 size_t siren_tc_section_bytes();   // siren_tc.cu
 size_t siren_rev_section_bytes();  // siren_rev.cu
 size_t siren_rev_workspace_bytes();
+size_t siren_mlp_section_bytes();  // siren_rev.cu
 
 inline bool siren_config_supported(int in_features, int hidden, int L, int out) {
     return hidden == kHidden && (in_features == 3 || in_features == 4) && out >= 1 && out <= kMaxOut && L >= 0 &&
@@ -114,6 +116,9 @@ inline SirenLayout siren_layout(int in_features, int hidden, int L, int out, int
     l.rev_ok = l.tc_ok && out == 1;
     l.off_rev = o;
     if (in_features == 3 && hidden == kHidden && L == 3 && out == 1) o += siren_rev_section_bytes();
+    // level classifier (exp_scripts/train_levels.py:35-51): reserved independently of the activation, like the TC section
+    l.mlp_ok = (in_features == 4 && hidden == kHidden && L == 1 && out <= 16 && activation == INF3DP_ACT_RELU);
+    if (in_features == 4 && hidden == kHidden && L == 1 && out <= 16) o += siren_mlp_section_bytes();
     l.total = align_up(o, 256);
     return l;
 }
@@ -130,6 +135,9 @@ int siren_rev_pack(const float* const* W, float omega0, const uint32_t* maxabs_b
                    SirenHeader& hdr, cudaStream_t stream);
 int siren_rev_launch(const void* packed, const SirenHeader& h, const float* x, int64_t n, float* y, float* J, void* ws,
                      size_t ws_bytes, cudaStream_t stream);
+int siren_mlp_pack(const float* const* W, const float* const* b, int out_features, void* packed, const SirenLayout& lay,
+                   SirenHeader& hdr, cudaStream_t stream);
+int siren_mlp_launch(const void* packed, const SirenHeader& h, const float* x, int64_t n, float* y, cudaStream_t stream);
 int siren_jet2_launch(const void* packed, const SirenHeader& h, const float* x, int64_t n, float* y, float* J, float* H,
                       cudaStream_t stream);
 

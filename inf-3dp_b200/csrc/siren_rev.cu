@@ -53,6 +53,13 @@ constexpr size_t kHalfImgBytes = 16 * kPerKBytes;
 constexpr size_t kGemmImgBytes = 2 * kHalfImgBytes;
 constexpr size_t kRevSectionBytes = kRevOffImg + 6 * kGemmImgBytes;
 
+// packed MLP section (level classifier 4 -> 256 -> 256 -> C, ReLU; same off_rev slot of the blob)
+constexpr size_t kMlpOffMisc = 0;           // float: [0] 1/S, uint32 at +64: max |W1| bits (pack-time scratch), float b2[16] at +128
+constexpr size_t kMlpOffW2 = 1024;          // float [256][16]: W2 transposed, columns >= C are zero
+constexpr size_t kMlpOffImg = 1024 + 16384; // one GEMM image (W1), 2 N-halves x 16 K-steps x (hi 4 KB, lo 4 KB)
+constexpr size_t kMlpSectionBytes = kMlpOffImg + 2 * 16 * 8192;
+constexpr int kMlpMaxOut = 16;
+
 constexpr int kEpiWarps = 16;
 constexpr int kProducerWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;
 constexpr int kThreads = (kEpiWarps + 2) * 32;  // 576
@@ -74,21 +81,29 @@ struct RevCfg {
                          kNumBars = 2 * kStages + 5;
     static constexpr uint32_t kSmemTmemPtr = kSmemBars + kNumBars * 8;
     static constexpr uint32_t kSmemTotal = kSmemTmemPtr + 16;
-    static_assert(kSmemTotal <= 232448 - 1024, "shared memory budget");
+    // KIND 2 only: W2^T [256][16] f32 and the partial logits [4 groups][16][128] f32
+    static constexpr uint32_t kSmemMlpW2 = (kSmemTotal + 255u) & ~255u;
+    static constexpr uint32_t kSmemMlpPart = kSmemMlpW2 + 16384;
+    static constexpr uint32_t kSmemTotalMlp = kSmemMlpPart + 32768;
+    static_assert(CTAS == 1 || kSmemTotalMlp <= 232448 - 1024, "shared memory budget");   // KIND 2 runs on CTA pairs only
 };
 
 // KIND 0: reverse-mode value + gradient (6 GEMMs per tile of 128 points).
 // KIND 1: forward-mode second-order jet, value + gradient + Hessian (diff_operators.py:27-44 hessian3d): 3 GEMMs per tile
 //         of 12 points x 10 jet rows (value, d/dx_i, d2/dx_i dx_j for ij in 00 01 02 11 12 22; 3 points per 32-lane
 //         quadrant of tensor memory, lanes 30 and 31 idle), same CTA-pair schedule, same weight images (GEMMs 0..2).
+// KIND 2: the level classifier of the collision query (exp_scripts/train_levels.py:35-51, utils.py:269-303): ReLU MLP
+//         4 -> 256 -> 256 -> C (C <= 16), value only.  One GEMM per tile of 128 points; layer 0 (4 -> 256) and the linear
+//         output layer (256 -> C, folded into the hidden layer's epilogue) are FP32 CUDA-core work.
 template <int CTAS, int KIND>
 __global__ void __launch_bounds__(kThreads, 1)
 siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __restrict__ x, int64_t n,
                  float* __restrict__ y, float* __restrict__ J, float* __restrict__ Hout, float4* __restrict__ stash,
                  unsigned long long* __restrict__ dbg) {
     using C = RevCfg<CTAS>;
-    constexpr int kGemms = KIND == 0 ? 6 : 3;
-    constexpr int kTilePts = KIND == 0 ? 128 : 12;
+    constexpr int kGemms = KIND == 0 ? 6 : (KIND == 1 ? 3 : 1);
+    constexpr int kTilePts = KIND == 1 ? 12 : 128;
+    constexpr size_t kImgBase = KIND == 2 ? kMlpOffImg : kRevOffImg;
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t sbase = (smem_u32(smem_dyn) + 1023u) & ~1023u;   // same offset in both CTAs of a pair
     unsigned char* sptr = smem_dyn + (sbase - smem_u32(smem_dyn));
@@ -118,7 +133,20 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
         mbar_init(bar(C::kBarDFull), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    {
+    if constexpr (KIND == 2) {
+        float4* s_w0 = reinterpret_cast<float4*>(sptr + C::kSmemW0);
+        const float4* g_w0 = reinterpret_cast<const float4*>(packed + h.off_w0);   // [256][4]: all four inputs are used
+        for (int i = tid; i < 256; i += kThreads) s_w0[i] = g_w0[i];
+        float* s_bias = reinterpret_cast<float*>(sptr + C::kSmemBias);
+        const float* g_b0 = reinterpret_cast<const float*>(packed + h.off_b0);
+        const float* g_b1 = reinterpret_cast<const float*>(packed + h.off_b);
+        for (int i = tid; i < 256; i += kThreads) { s_bias[i] = g_b0[i]; s_bias[256 + i] = g_b1[i]; }
+        float4* s_w2 = reinterpret_cast<float4*>(sptr + C::kSmemMlpW2);
+        const float4* g_w2 = reinterpret_cast<const float4*>(rv + kMlpOffW2);
+        for (int i = tid; i < 256 * 4; i += kThreads) s_w2[i] = g_w2[i];
+        float* s_misc = reinterpret_cast<float*>(sptr + C::kSmemMisc);
+        if (tid == 0) s_misc[0] = reinterpret_cast<const float*>(rv + kMlpOffMisc)[0];             // 1/S of the hidden layer
+    } else {
         float4* s_w0 = reinterpret_cast<float4*>(sptr + C::kSmemW0);
         const float* g_w0 = reinterpret_cast<const float*>(packed + h.off_w0);
         const float* g_b0 = reinterpret_cast<const float*>(packed + h.off_b0);
@@ -158,7 +186,7 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
             uint32_t stage = 0, phase = 0;
             for (int it = 0; it < my_units; ++it) {
                 for (int g = 0; g < kGemms; ++g) {
-                    const char* img = rv + kRevOffImg + (size_t)g * kGemmImgBytes;
+                    const char* img = rv + kImgBase + (size_t)g * kGemmImgBytes;
                     for (int r = 0; r < 4; ++r) {
                         mbar_wait(bar(C::kBarWEmpty + stage), phase ^ 1u);
                         const uint32_t dst = sbase + C::kSmemRing + stage * C::kStageBytes;
@@ -273,7 +301,88 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
             if (lane == 0) { if (CTAS == 2) mbar_arrive_cluster(a_ready_addr[mi]); else mbar_arrive(a_ready_addr[mi]); }
         };
 
-        if constexpr (KIND == 1) {
+        if constexpr (KIND == 2) {
+        // ---------------- ReLU level classifier: 128 points per tile, one GEMM --------------------------------------------------
+        const float4* s_w2 = reinterpret_cast<const float4*>(sptr + C::kSmemMlpW2);   // [256][4 float4] = W2^T rows of 16
+        float* s_lpart = reinterpret_cast<float*>(sptr + C::kSmemMlpPart);            // [4][16][128]
+        const int out_f = h.out_features;
+        for (int it = 0; it < my_units; ++it) {
+            const int64_t tile = (unit0 + (int64_t)it * unit_stride) * CTAS + rank;
+            const int64_t pt = tile * 128 + row;
+            const bool pvalid = pt < n;
+            float4 xin = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (pvalid) xin = reinterpret_cast<const float4*>(x)[pt];
+            // layer 0 (FP32): a0 = relu(W0 x + b0)
+#pragma unroll 1
+            for (int mi = 0; mi < 4; ++mi) {
+                const int m = grp + 4 * mi;
+                uint32_t o[16];
+#pragma unroll
+                for (int i = 0; i < 16; i += 2) {
+                    float r2[2];
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const int f = 16 * m + i + u;
+                        const float4 w = s_w0[f];
+                        // x W^T + b in the accumulation order of a row-major dot product (k = 0..3), then the bias
+                        const float z = fmaf(w.w, xin.w, fmaf(w.z, xin.z, fmaf(w.y, xin.y, w.x * xin.x))) + s_bias[f];
+                        r2[u] = fmaxf(z, 0.f);
+                    }
+                    split_pack<true>(r2[0], r2[1], o[i >> 1], o[8 + (i >> 1)]);
+                }
+                TC_ST16(regionP + lane_off + 16u * (uint32_t)m, o);
+                publish(mi);
+            }
+            float acc[kMlpMaxOut];
+#pragma unroll
+            for (int o = 0; o < kMlpMaxOut; ++o) acc[o] = 0.f;
+            {
+                const float inv = s_misc[0];
+                mbar_wait_warp(bar(C::kBarDFull), dphase, lane, pd);
+                dphase ^= 1u;
+                tc_fence_after();
+                uint32_t v[16];
+                TC_LD16(regionQ + lane_off + 16u * (uint32_t)grp, v);
+#pragma unroll 1
+                for (int mi = 0; mi < 4; ++mi) {
+                    const int m = grp + 4 * mi;
+                    tc_wait_ld();
+                    float cur[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) cur[i] = __uint_as_float(v[i]);
+                    if (mi < 3) TC_LD16(regionQ + lane_off + 16u * (uint32_t)(m + 4), v);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int f = 16 * m + i;
+                        const float a = fmaxf(fmaf(cur[i], inv, s_bias[256 + f]), 0.f);
+#pragma unroll
+                        for (int q = 0; q < kMlpMaxOut / 4; ++q) {
+                            if (4 * q < out_f) {   // uniform
+                                const float4 w = s_w2[4 * f + q];
+                                acc[4 * q] = fmaf(a, w.x, acc[4 * q]);
+                                acc[4 * q + 1] = fmaf(a, w.y, acc[4 * q + 1]);
+                                acc[4 * q + 2] = fmaf(a, w.z, acc[4 * q + 2]);
+                                acc[4 * q + 3] = fmaf(a, w.w, acc[4 * q + 3]);
+                            }
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int o = 0; o < kMlpMaxOut; ++o) s_lpart[(grp * kMlpMaxOut + o) * 128 + row] = acc[o];
+            asm volatile("bar.sync 1, 512;" ::: "memory");
+            // 512 threads write the 128 x C logits: thread (row, grp) sums the partials of outputs grp, grp + 4, ...
+            if (pvalid) {
+                const float* b2 = reinterpret_cast<const float*>(rv + kMlpOffMisc + 128);
+                for (int o = grp; o < out_f; o += 4) {
+                    const float val = ((s_lpart[(0 * kMlpMaxOut + o) * 128 + row] + s_lpart[(1 * kMlpMaxOut + o) * 128 + row]) +
+                                       s_lpart[(2 * kMlpMaxOut + o) * 128 + row]) + s_lpart[(3 * kMlpMaxOut + o) * 128 + row];
+                    y[pt * out_f + o] = val + b2[o];
+                }
+            }
+            asm volatile("bar.sync 1, 512;" ::: "memory");   // the partials are rewritten by the next tile's epilogue
+        }
+        } else if constexpr (KIND == 1) {
         // ---------------- second-order forward jet: 3 points x 10 rows per quadrant ------------------------------------------
         const int pl = lane / 10;                       // point of the quadrant (3 = idle lanes 30, 31)
         const int c = lane - 10 * pl;                   // jet row: 0 value, 1..3 d/dx_i, 4..9 d2/dx_i dx_j
@@ -579,14 +688,32 @@ __global__ void rev_pack_out_kernel(const float* __restrict__ W4, const uint32_t
     if (f < 256) reinterpret_cast<float2*>(rv + kRevOffW4)[f] = make_float2(W4[f], G * W4[f]);
 }
 
+__global__ void mlp_maxabs_kernel(const float* __restrict__ W, int count, uint32_t* __restrict__ slot) {
+    float m = 0.f;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) m = fmaxf(m, fabsf(W[i]));
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(slot, __float_as_uint(m));
+}
+
+__global__ void mlp_pack_out_kernel(const float* __restrict__ W2, const float* __restrict__ b2, int out_f, char* __restrict__ rv) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // f * 16 + o
+    const uint32_t* mx = reinterpret_cast<const uint32_t*>(rv + kMlpOffMisc + 64);
+    if (idx == 0) reinterpret_cast<float*>(rv + kMlpOffMisc)[0] = 1.f / pow2_scale_to(__uint_as_float(*mx), 4);
+    if (idx < kMlpMaxOut) reinterpret_cast<float*>(rv + kMlpOffMisc + 128)[idx] = idx < out_f ? b2[idx] : 0.f;
+    if (idx < 256 * kMlpMaxOut) {
+        const int f = idx / kMlpMaxOut, o = idx % kMlpMaxOut;
+        reinterpret_cast<float*>(rv + kMlpOffW2)[idx] = o < out_f ? W2[o * 256 + f] : 0.f;
+    }
+}
+
 template <int CTAS, int KIND>
 int launch_rev(const void* packed, const SirenHeader& h, const float* x, int64_t n, float* y, float* J, float* H, void* ws,
                cudaStream_t stream) {
     using C = RevCfg<CTAS>;
     auto kern = siren_rev_kernel<CTAS, KIND>;
-    const int smem = (int)C::kSmemTotal + 1024;
+    const int smem = (int)(KIND == 2 ? C::kSmemTotalMlp : C::kSmemTotal) + 1024;
     INF3DP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    constexpr int kTilePts = KIND == 0 ? 128 : 12;
+    constexpr int kTilePts = KIND == 1 ? 12 : 128;
     const int64_t tiles = (n + kTilePts - 1) / kTilePts;
     const int64_t units = (tiles + CTAS - 1) / CTAS;
     const int64_t max_units = num_sms() / CTAS;
@@ -622,7 +749,7 @@ int launch_rev(const void* packed, const SirenHeader& h, const float* x, int64_t
                     hbuf[33 + g * 4] / u, hbuf[34 + g * 4] / u, hbuf[35 + g * 4] / u);
         fprintf(stderr, "[inf3dp rev debug] CTAS=%d KIND=%d block0: %.0f units, %.0f cyc/unit (%d GEMMs); MMA thread blocked on a_ready %.0f, "
                         "on w_full %.0f cyc/unit; epilogue warp0 blocked on d_full %.0f, warp5 %.0f, warp15 %.0f cyc/unit\n",
-                CTAS, KIND, u, hbuf[0] / u, KIND == 0 ? 6 : 3, hbuf[1] / u, hbuf[2] / u, hbuf[8] / u, hbuf[13] / u, hbuf[23] / u);
+                CTAS, KIND, u, hbuf[0] / u, KIND == 0 ? 6 : (KIND == 1 ? 3 : 1), hbuf[1] / u, hbuf[2] / u, hbuf[8] / u, hbuf[13] / u, hbuf[23] / u);
     }
     return INF3DP_OK;
 }
@@ -630,6 +757,29 @@ int launch_rev(const void* packed, const SirenHeader& h, const float* x, int64_t
 }  // namespace
 
 size_t siren_rev_section_bytes() { return kRevSectionBytes; }
+
+size_t siren_mlp_section_bytes() { return kMlpSectionBytes; }
+
+int siren_mlp_pack(const float* const* W, const float* const* b, int out_features, void* packed, const SirenLayout& lay,
+                   SirenHeader& hdr, cudaStream_t stream) {
+    char* rv = (char*)packed + lay.off_rev;
+    INF3DP_CUDA(cudaMemsetAsync(rv, 0, kMlpOffW2, stream));
+    uint32_t* mx = reinterpret_cast<uint32_t*>(rv + kMlpOffMisc + 64);
+    mlp_maxabs_kernel<<<64, 256, 0, stream>>>(W[1], 256 * 256, mx);
+    INF3DP_LAUNCH_CHECK("mlp_maxabs_kernel");
+    rev_pack_gemm_kernel<<<256, 256, 0, stream>>>(W[1], 1.f, mx, 0, rv + kMlpOffImg);
+    INF3DP_LAUNCH_CHECK("rev_pack_gemm_kernel");
+    mlp_pack_out_kernel<<<(256 * kMlpMaxOut + 255) / 256, 256, 0, stream>>>(W[2], b[2], out_features, rv);
+    INF3DP_LAUNCH_CHECK("mlp_pack_out_kernel");
+    hdr.mlp_ok = 1;
+    return INF3DP_OK;
+}
+
+int siren_mlp_launch(const void* packed, const SirenHeader& h, const float* x, int64_t n, float* y, cudaStream_t stream) {
+    INF3DP_CHECK_ARG(h.mlp_ok && h.off_rev != 0, "siren_mlp: packed weights carry no classifier operand image");
+    INF3DP_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0, "siren_mlp: x must be 16-byte aligned ([n,4] rows are read as float4)");
+    return launch_rev<2, 2>(packed, h, x, n, y, nullptr, nullptr, nullptr, stream);
+}
 
 size_t siren_rev_workspace_bytes() { return (size_t)num_sms() * kStashBytesPerCta; }
 

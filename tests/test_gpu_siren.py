@@ -114,13 +114,32 @@ def test_reference_call_pattern_autograd(golden):
 
 
 def test_level_mlp_relu(golden):
+    """exp_scripts/train_levels.py:35-51 logits: the tensor-core classifier engine (default) and the FP32 SIMT engine
+    against the logits recorded from the reference; ragged sizes; C = 3 (the reference's default) and C = 8."""
     import inf3dp
     lvl = inf3dp.MLPClassifier(num_classes=8)
     lvl.load_state_dict({k[len("level/"):]: torch.from_numpy(np.asarray(golden[k])) for k in golden.files if k.startswith("level/network")})
     lvl.cuda()
-    lo = lvl(torch.from_numpy(golden["level/x"]).cuda()).cpu().numpy()
+    xg = torch.from_numpy(golden["level/x"]).cuda()
+    lo = lvl(xg).cpu().numpy()
     assert np.abs(lo - golden["level/logits"]).max() < 1e-5
     assert np.array_equal(lo.argmax(-1), golden["level/logits"].argmax(-1))
+    ls, _, _ = lvl.query(xg, order=0, mode="simt")
+    assert np.abs(ls.cpu().numpy() - golden["level/logits"]).max() < 1e-5
+    for n in (1, 127, 129, 300, 70001):
+        g = torch.Generator().manual_seed(n)
+        x = (torch.rand(n, 4, generator=g) * 2 - 1).cuda()
+        a = lvl(x)
+        b, _, _ = lvl.query(x, order=0, mode="simt")
+        assert a.shape == (n, 8) and torch.isfinite(a).all()
+        assert (a - b).abs().max().item() < 2e-5
+        if n > 200:
+            assert torch.equal(lvl(x[77:]), a[77:])
+    torch.manual_seed(3)
+    l3 = inf3dp.MLPClassifier(num_classes=3).cuda()
+    x = (torch.rand(5000, 4) * 2 - 1).cuda()
+    ref = l3.network(x)   # plain torch modules (cuBLAS FP32) as the reference of the same weights
+    assert (l3(x) - ref).abs().max().item() < 2e-5
 
 
 @pytest.mark.parametrize("engine", ENGINES_GRAD1)
