@@ -68,7 +68,8 @@ int inf3dp_siren_pack_weights(const float* const* weights_host, const float* con
  * Derivatives are taken with respect to the first three input features.  J / H may be NULL when order is lower.
  * mode: INF3DP_MODE_*.  TC modes need the flagship configuration (sine, in 3, hidden 256, 3 hidden layers,
  * out <= 4) with order <= 1, or out == 1 with order == 2 (second-order jet on tensor-core CTA pairs: 10 jet rows per
- * point), and return INF3DP_EINVAL otherwise; AUTO falls back to SIMT for everything else. */
+ * point), or the ReLU classifier in 4 / one hidden layer / out <= 16 with order 0 (x must then be 16-byte aligned), and
+ * return INF3DP_EINVAL otherwise; AUTO falls back to SIMT for everything else. */
 int inf3dp_siren_jet(const void* packed, const float* x, int64_t n, int order, float* y, float* J, float* H,
                      int mode, inf3dp_stream_t stream);
 
