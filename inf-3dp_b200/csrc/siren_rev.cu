@@ -676,9 +676,31 @@ __global__ void rev_pack_gemm_kernel(const float* __restrict__ W, float omega0, 
     *reinterpret_cast<__half*>(img + off + 4096) = lo;
 }
 
+// Column abs-sum norm of one hidden layer, omega folded: max_k sum_n |W'[n][k]| -- the factor by which the backward
+// sweep can at most amplify max |g| through this layer.  misc[8 + l] receives it.
+__global__ void rev_colnorm_kernel(const float* __restrict__ W, float omega0, float* __restrict__ out) {
+    __shared__ float s_m[8];
+    const int k = threadIdx.x;   // 256 threads = 256 columns
+    float sum = 0.f;
+    for (int nrow = 0; nrow < 256; ++nrow) sum += fabsf(omega0 * W[nrow * 256 + k]);
+    for (int o = 16; o > 0; o >>= 1) sum = fmaxf(sum, __shfl_xor_sync(0xffffffffu, sum, o));
+    if ((k & 31) == 0) s_m[k >> 5] = sum;
+    __syncthreads();
+    if (k == 0) { float m = s_m[0]; for (int i = 1; i < 8; ++i) m = fmaxf(m, s_m[i]); *out = m; }
+}
+
 __global__ void rev_pack_out_kernel(const float* __restrict__ W4, const uint32_t* __restrict__ maxabs_bits,
                                     char* __restrict__ rv) {
-    const float G = pow2_scale_to(__uint_as_float(*maxabs_bits), 1);   // max |G w4| in [1, 2): 2^15 of FP16 headroom
+    // Range scale of the backward sweep.  max |G w4| in [1, 2) leaves 2^15 of FP16 headroom, which random-init and
+    // typical trained fields never approach (measured max |G g| ~ 4); if the worst-case amplification of the three
+    // layers (product of their column abs-sum norms) could exceed it, G is lowered by the missing power of two, so
+    // the hi parts can never overflow (the lo parts then lose that many bits instead).
+    float G = pow2_scale_to(__uint_as_float(*maxabs_bits), 1);
+    {
+        const float* norms = reinterpret_cast<const float*>(rv + kRevOffMisc) + 8;
+        const float worst = 2.f * norms[0] * norms[1] * norms[2];   // bound on max |G g_0| with max |G w4| < 2
+        if (worst > 32768.f && isfinite(worst)) { int e; frexpf(worst / 32768.f, &e); G = ldexpf(G, -e); }
+    }
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f == 0) {
         float* misc = reinterpret_cast<float*>(rv + kRevOffMisc);
@@ -793,6 +815,10 @@ int siren_rev_pack(const float* const* W, float omega0, const uint32_t* maxabs_b
         rev_pack_gemm_kernel<<<256, 256, 0, stream>>>(W[layer], omega0, maxabs_bits + (layer - 1), g >= 3 ? 1 : 0,
                                                       rv + kRevOffImg + (size_t)g * kGemmImgBytes);
         INF3DP_LAUNCH_CHECK("rev_pack_gemm_kernel");
+    }
+    for (int l = 1; l <= 3; ++l) {
+        rev_colnorm_kernel<<<1, 256, 0, stream>>>(W[l], omega0, reinterpret_cast<float*>(rv + kRevOffMisc) + 8 + (l - 1));
+        INF3DP_LAUNCH_CHECK("rev_colnorm_kernel");
     }
     rev_pack_out_kernel<<<1, 256, 0, stream>>>(W[4], maxabs_bits + 3, rv);
     INF3DP_LAUNCH_CHECK("rev_pack_out_kernel");
