@@ -144,6 +144,48 @@ int inf3dp_fields_intersection(const float* slice_fields, const float* lattice1_
                                uint8_t* inter_mask, int16_t* isovalue_indices, float* intersections,
                                void* workspace, size_t workspace_bytes, inf3dp_stream_t stream);
 
+
+/* The same operation on the SAMPLE GRIDS themselves.  Replaces, in one call, the reference's host-side preparation
+ * toolpath_utils.py:986-1019 extract_corner_fields (8x corner expansion of each [N,N,N] grid) and :1021-1033
+ * get_voxel_centers, followed by ext.cpp:20-46: grids [Gx,Gy,Gz] f32 (voxels = (Gx-1)(Gy-1)(Gz-1), corner c of voxel
+ * (x,y,z) = grid[x+(c&1), y+((c>>1)&1), z+((c>>2)&1)], centre = (index + 0.5) * float(2/(Gx-1)) - 1 rounded as
+ * torch does), same outputs, bit-identical to inf3dp_fields_intersection on the expanded tensors.
+ * Workspace: inf3dp_fields_intersection_workspace_bytes(Gx-1, Gy-1, Gz-1, Ns, N1, N2). */
+int inf3dp_fields_intersection_grid(const float* slice_grid, const float* lattice1_grid, const float* lattice2_grid,
+                                    const float* slice_iso, const float* lattice1_iso, const float* lattice2_iso,
+                                    int Gx, int Gy, int Gz, int Ns, int N1, int N2, uint8_t* inter_mask,
+                                    int16_t* isovalue_indices, float* intersections, void* workspace,
+                                    size_t workspace_bytes, inf3dp_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Query grid.  Replaces sdf_meshing.py:46-65 gen_voxle_queries for an index range: out [count,3] f32 holds rows
+ * [start, start+count) of the reference's [N^3,3] tensor, bit-identical INCLUDING the true-division shear of
+ * :57-58.  A grid sweep therefore never materialises the 12*N^3-byte coordinate tensor.
+ * ------------------------------------------------------------------------------------------------------- */
+int inf3dp_grid_queries(int N, float cube_size, int64_t start, int64_t count, float* out, inf3dp_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Marching cubes on a sample grid.  Replaces the host call skimage.measure.marching_cubes(volume, level, spacing)
+ * at sdf_meshing.py:399 (convert_sdf_samples_to_ply) and utils.py:322 (gen_iso_layers); same return values:
+ *   verts [nv,3] f32 (index coordinates * spacing), faces [nf,3] i32, normals [nv,3] f32 (normalised grid gradient),
+ *   values [nv] f32 (larger of the two samples of the vertex's edge).
+ * One welded vertex per sign-changing grid edge; cubes with a non-finite corner are skipped (NaN-masked volumes,
+ * utils.py:308); `descent` != 0 orients triangles and normals towards decreasing values (skimage's default
+ * gradient_direction), 0 towards increasing values.  Deterministic output order (linear sample order, z fastest).
+ * Two phases because the sizes are data dependent:
+ *   _count  classifies, leaves per-tile counts/offsets in the workspace, SYNCHRONISES the stream and returns
+ *           counts_host[0] = nv, counts_host[1] = nf
+ *   _emit   writes the arrays (normals / values may be NULL); needs the workspace left by _count for the same
+ *           volume and level.
+ * ------------------------------------------------------------------------------------------------------- */
+size_t inf3dp_marching_cubes_workspace_bytes(int Gx, int Gy, int Gz);
+int inf3dp_marching_cubes_count(const float* volume, int Gx, int Gy, int Gz, float level, void* workspace,
+                                size_t workspace_bytes, int64_t* counts_host, inf3dp_stream_t stream);
+int inf3dp_marching_cubes_emit(const float* volume, int Gx, int Gy, int Gz, float level, float spacing_x,
+                               float spacing_y, float spacing_z, int descent, float* verts, int32_t* faces,
+                               float* normals, float* values, int64_t n_verts, int64_t n_faces, void* workspace,
+                               size_t workspace_bytes, inf3dp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

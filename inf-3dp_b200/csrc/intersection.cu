@@ -9,9 +9,10 @@
 //   * the three isovalue arrays are rank-sorted once, so a voxel binary-searches its three index windows instead
 //     of the reference's 128 + 128*h1 + Ns*h1*h2 linear scans
 //   * the reference lets voxels that hit the same cell race (last writer wins, :119-124, :216-218); here pass 1
-//     elects the LOWEST linear voxel index per cell with atomicMin and pass 2 -- run only over the compacted
-//     list of voxels that hit anything -- lets the winner write.  Deterministic, one full read of the fields.
-//   * outputs are initialised by the same call (mask 0, indices -1, points 0), 16-byte vectorised
+//     elects the LOWEST linear voxel index per cell with atomicMin and pass 2 -- one thread per CELL -- evaluates
+//     the winner voxel for that cell (or writes the defaults).  Deterministic, one full read of the fields.
+//   * inf3dp_fields_intersection_grid reads the three [N,N,N] sample grids directly: the reference's host-side
+//     8x corner expansion (toolpath_utils.py:986-1019) and voxel-centre tensor (:1021-1033) are never built
 #include <algorithm>
 
 #include "common.cuh"
@@ -20,11 +21,10 @@ namespace inf3dp {
 namespace {
 
 struct IsectWs {
-    int* hdr;         // [0] number of voxels in the work list, [4..6] finite isovalue counts (slice, l1, l2)
+    int* hdr;         // [4..6] finite isovalue counts (slice, l1, l2)
     float* iso_sorted[3];
     int* iso_perm[3];
     int* winner;      // [cells]
-    int* worklist;    // [voxels]
     size_t total_bytes;
 };
 
@@ -40,7 +40,7 @@ IsectWs carve_isect(void* base, long long voxels, long long cells, int Ns, int N
         w.iso_perm[i] = (int*)(b + take((size_t)(n[i] > 0 ? n[i] : 1) * 4));
     }
     w.winner = (int*)(b + take((size_t)cells * 4));
-    w.worklist = (int*)(b + take((size_t)voxels * 4));
+    (void)voxels;
     w.total_bytes = o;
     return w;
 }
@@ -145,14 +145,91 @@ struct VoxelFields {
     float4 s[2], a[2], b[2];
 };
 
-__device__ __forceinline__ void load_voxel(const float* __restrict__ sf, const float* __restrict__ af,
-                                           const float* __restrict__ bf, long long v, VoxelFields& f) {
-    const float4* sp = reinterpret_cast<const float4*>(sf) + 2 * v;
-    const float4* ap = reinterpret_cast<const float4*>(af) + 2 * v;
-    const float4* bp = reinterpret_cast<const float4*>(bf) + 2 * v;
-    f.s[0] = __ldcs(sp); f.s[1] = __ldcs(sp + 1);
-    f.a[0] = __ldcs(ap); f.a[1] = __ldcs(ap + 1);
-    f.b[0] = __ldcs(bp); f.b[1] = __ldcs(bp + 1);
+// Where the corner values of a voxel come from.  GRID = false: the reference's corner-expanded [Dx,Dy,Dz,8] tensors
+// (32 B per voxel and field) and its [Dx,Dy,Dz,3] voxel centres.  GRID = true: the [Dx+1,Dy+1,Dz+1] sample grids
+// themselves (4 B per voxel and field from HBM, neighbours through L1/L2) -- the expansion of
+// toolpath_utils.py:986-1019 (corner c = offsets (c&1, (c>>1)&1, (c>>2)&1) on the three grid axes) and the centres of
+// toolpath_utils.py:1021-1033 are evaluated on the fly, bit-identically.
+struct FieldSrc {
+    const float *sf, *af, *bf;
+    const float* centers;   // expanded mode only
+    int Dy, Dz;             // voxel counts on axes 1, 2
+    long long sx, sy;       // grid strides of axes 0, 1 (axis 2 is contiguous)
+    float center_vs;        // (float)(2.0 / (Gx - 1)): get_voxel_centers' voxel size as torch applies it to a float32 tensor
+};
+
+__device__ __forceinline__ void voxel_xyz(const FieldSrc& src, unsigned v, int& x, int& y, int& z) {
+    const unsigned u = v / (unsigned)src.Dz;    // voxels < 2^31: 32-bit index arithmetic
+    z = (int)(v - u * (unsigned)src.Dz);
+    x = (int)(u / (unsigned)src.Dy);
+    y = (int)(u - (unsigned)x * (unsigned)src.Dy);
+}
+
+__device__ __forceinline__ void load_plane(const FieldSrc& src, long long b, float4& s, float4& a, float4& bb) {
+    const long long o1 = b + src.sx, o2 = b + src.sy, o3 = o1 + src.sy;
+    s = make_float4(__ldg(src.sf + b), __ldg(src.sf + o1), __ldg(src.sf + o2), __ldg(src.sf + o3));
+    a = make_float4(__ldg(src.af + b), __ldg(src.af + o1), __ldg(src.af + o2), __ldg(src.af + o3));
+    bb = make_float4(__ldg(src.bf + b), __ldg(src.bf + o1), __ldg(src.bf + o2), __ldg(src.bf + o3));
+}
+
+// one voxel by index (gather): expanded tensors or grids
+template <bool GRID, bool STREAM>
+__device__ __forceinline__ void load_voxel(const FieldSrc& src, long long v, VoxelFields& f) {
+    if (GRID) {
+        int x, y, z;
+        voxel_xyz(src, (unsigned)v, x, y, z);
+        const long long b = x * src.sx + y * src.sy + z;
+        load_plane(src, b, f.s[0], f.a[0], f.b[0]);
+        load_plane(src, b + 1, f.s[1], f.a[1], f.b[1]);
+    } else {
+        const float4* sp = reinterpret_cast<const float4*>(src.sf) + 2 * v;
+        const float4* ap = reinterpret_cast<const float4*>(src.af) + 2 * v;
+        const float4* bp = reinterpret_cast<const float4*>(src.bf) + 2 * v;
+        if (STREAM) {
+            f.s[0] = __ldcs(sp); f.s[1] = __ldcs(sp + 1);
+            f.a[0] = __ldcs(ap); f.a[1] = __ldcs(ap + 1);
+            f.b[0] = __ldcs(bp); f.b[1] = __ldcs(bp + 1);
+        } else {
+            f.s[0] = __ldg(sp); f.s[1] = __ldg(sp + 1);
+            f.a[0] = __ldg(ap); f.a[1] = __ldg(ap + 1);
+            f.b[0] = __ldg(bp); f.b[1] = __ldg(bp + 1);
+        }
+    }
+}
+
+__device__ __forceinline__ float4 shfl_down4(const float4 v) {
+    return make_float4(__shfl_down_sync(0xffffffffu, v.x, 1), __shfl_down_sync(0xffffffffu, v.y, 1),
+                       __shfl_down_sync(0xffffffffu, v.z, 1), __shfl_down_sync(0xffffffffu, v.w, 1));
+}
+
+// grids, consecutive lanes = consecutive voxels (called by all 32 lanes): a lane loads the four corners of its lower z
+// plane per field; its upper plane is the next lane's lower plane (shuffle) unless the row or the warp ends there
+__device__ __forceinline__ void load_voxel_grid_warp(const FieldSrc& src, long long v, bool active, VoxelFields& f) {
+    int x = 0, y = 0, z = 0;
+    long long b = 0;
+    f.s[0] = f.a[0] = f.b[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (active) {
+        voxel_xyz(src, (unsigned)v, x, y, z);
+        b = x * src.sx + y * src.sy + z;
+        load_plane(src, b, f.s[0], f.a[0], f.b[0]);
+    }
+    f.s[1] = shfl_down4(f.s[0]);
+    f.a[1] = shfl_down4(f.a[0]);
+    f.b[1] = shfl_down4(f.b[0]);
+    if (active && ((threadIdx.x & 31) == 31 || z + 1 == src.Dz)) load_plane(src, b + 1, f.s[1], f.a[1], f.b[1]);
+}
+
+template <bool GRID>
+__device__ __forceinline__ void load_center(const FieldSrc& src, long long v, float* ctr) {
+    if (GRID) {   // (index + 0.5) * voxel_size + (-1), each step rounded to float32 as torch does
+        int x, y, z;
+        voxel_xyz(src, (unsigned)v, x, y, z);
+        ctr[0] = __fadd_rn(__fmul_rn((float)x + 0.5f, src.center_vs), -1.0f);
+        ctr[1] = __fadd_rn(__fmul_rn((float)y + 0.5f, src.center_vs), -1.0f);
+        ctr[2] = __fadd_rn(__fmul_rn((float)z + 0.5f, src.center_vs), -1.0f);
+    } else {
+        ctr[0] = __ldg(src.centers + 3ll * v); ctr[1] = __ldg(src.centers + 3ll * v + 1); ctr[2] = __ldg(src.centers + 3ll * v + 2);
+    }
 }
 
 struct Windows {
@@ -179,18 +256,19 @@ __device__ __forceinline__ Windows voxel_windows(const VoxelFields& f, const Iso
 }
 
 // pass 1: elect the winner voxel of every cell, compact the voxels that hit anything.
+template <bool GRID>
 __global__ void __launch_bounds__(256)
-isect_elect_kernel(const float* __restrict__ sf, const float* __restrict__ af, const float* __restrict__ bf,
-                   long long voxels, int Ns, int N1, int N2, IsectWs w) {
+isect_elect_kernel(const FieldSrc src, long long voxels, int Ns, int N1, int N2, IsectWs w) {
     extern __shared__ unsigned char s_tab[];
     const IsoTables tb = load_tables(w, s_tab, Ns, N1, N2);
     // persistent blocks: the tables are staged once per block, voxels are visited in block-sized strides
     for (long long base = (long long)blockIdx.x * blockDim.x; base < voxels; base += (long long)gridDim.x * blockDim.x) {
     const long long v = base + threadIdx.x;
     bool hit = false;
+    VoxelFields f;
+    if (GRID) load_voxel_grid_warp(src, v, v < voxels, f);
     if (v < voxels) {
-        VoxelFields f;
-        load_voxel(sf, af, bf, v, f);
+        if (!GRID) load_voxel<false, true>(src, v, f);
         const Windows r = voxel_windows(f, tb);
         if (r.any) {
             hit = true;
@@ -251,9 +329,9 @@ __device__ __forceinline__ int edge_sum(const float4 lo, const float4 hi, float 
 // winner voxels (a voxel typically spans 2-3 neighbouring slice isovalues), which the L1 serves.
 constexpr int kCellTileS = 8, kCellTile2 = 32;
 
+template <bool GRID>
 __global__ void __launch_bounds__(256)
-isect_cell_kernel(const float* __restrict__ sf, const float* __restrict__ af, const float* __restrict__ bf,
-                  const float* __restrict__ centers, const float* __restrict__ s_iso, const float* __restrict__ a_iso,
+isect_cell_kernel(const FieldSrc src, const float* __restrict__ s_iso, const float* __restrict__ a_iso,
                   const float* __restrict__ b_iso, int Dx, int Ns, int N1, int N2, long long tiles, IsectWs w,
                   uint8_t* __restrict__ mask, int16_t* __restrict__ idx, float* __restrict__ pts) {
     const float vs = (float)(2.0 / (double)(float)Dx);  // intersection.cu:54
@@ -275,15 +353,9 @@ isect_cell_kernel(const float* __restrict__ sf, const float* __restrict__ af, co
             continue;
         }
         VoxelFields f;
-        {
-            const float4* sp = reinterpret_cast<const float4*>(sf) + 2ll * v;
-            const float4* ap = reinterpret_cast<const float4*>(af) + 2ll * v;
-            const float4* bp = reinterpret_cast<const float4*>(bf) + 2ll * v;
-            f.s[0] = __ldg(sp); f.s[1] = __ldg(sp + 1);
-            f.a[0] = __ldg(ap); f.a[1] = __ldg(ap + 1);
-            f.b[0] = __ldg(bp); f.b[1] = __ldg(bp + 1);
-        }
-        const float ctr[3] = {__ldg(centers + 3ll * v), __ldg(centers + 3ll * v + 1), __ldg(centers + 3ll * v + 2)};
+        load_voxel<GRID, false>(src, v, f);
+        float ctr[3];
+        load_center<GRID>(src, v, ctr);
         float pa[3], pb[3], ps[3];
         const int ca = edge_sum(f.a[0], f.a[1], a_iso[i1], ctr, vs, pa);
         const int cb = edge_sum(f.b[0], f.b[1], b_iso[i2], ctr, vs, pb);
@@ -298,6 +370,49 @@ isect_cell_kernel(const float* __restrict__ sf, const float* __restrict__ af, co
             pts[3 * c + d] = (float)((double)(xs + xa + xb) / 3.0);
         }
     }
+}
+
+template <bool GRID>
+int isect_run(const FieldSrc& src, const float* s_iso, const float* a_iso, const float* b_iso, int Dx, int Dy, int Dz,
+              int Ns, int N1, int N2, uint8_t* mask, int16_t* idx, float* pts, void* ws, size_t ws_bytes,
+              inf3dp_stream_t stream) {
+    INF3DP_CHECK_ARG(Dx >= 0 && Dy >= 0 && Dz >= 0 && Ns >= 0 && N1 >= 0 && N2 >= 0, "fields_intersection: negative size");
+    const long long voxels = (long long)Dx * Dy * Dz, cells = (long long)Ns * N1 * N2;
+    if (cells == 0) return INF3DP_OK;
+    INF3DP_CHECK_ARG(voxels < 0x7fffffffll, "fields_intersection: %lld voxels exceed the int32 voxel index", voxels);
+    INF3DP_CHECK_ARG(Ns <= 32767 && N1 <= 32767 && N2 <= 32767,
+                     "fields_intersection: isovalue counts must fit the int16 index output (intersection.cu:247)");
+    INF3DP_CHECK_ARG(mask && idx && pts && ws && s_iso && a_iso && b_iso, "fields_intersection: null pointer");
+    INF3DP_CHECK_ARG(voxels == 0 || (src.sf && src.af && src.bf), "fields_intersection: null pointer");
+    INF3DP_CHECK_ARG(((reinterpret_cast<uintptr_t>(pts) | reinterpret_cast<uintptr_t>(idx) |
+                       reinterpret_cast<uintptr_t>(mask)) & 15) == 0,
+                     "fields_intersection: field and output pointers must be 16-byte aligned");
+    IsectWs w = carve_isect(ws, voxels > 0 ? voxels : 1, cells, Ns, N1, N2);
+    if (ws_bytes < w.total_bytes) {
+        set_error("fields_intersection: workspace has %zu bytes, need %zu", ws_bytes, w.total_bytes);
+        return INF3DP_EWORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    isect_prep_kernel<<<1, 1024, 0, st>>>(s_iso, a_iso, b_iso, Ns, N1, N2, w);
+    INF3DP_LAUNCH_CHECK("isect_prep_kernel");
+    const long long quads = (cells + 3) / 4;
+    isect_init_kernel<<<(unsigned)((quads + 255) / 256), 256, 0, st>>>(cells, w.winner);
+    INF3DP_LAUNCH_CHECK("isect_init_kernel");
+    if (voxels > 0) {
+        const size_t tab_smem = (Ns + N1 + N2) <= kMaxTableEntries ? (size_t)(Ns + N1 + N2) * 8 : 0;
+        if (tab_smem > 40 * 1024) {
+            INF3DP_CUDA(cudaFuncSetAttribute(isect_elect_kernel<GRID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tab_smem));
+        }
+        isect_elect_kernel<GRID><<<(unsigned)std::min<long long>((voxels + 255) / 256, (long long)num_sms() * 16), 256, tab_smem, st>>>(src, voxels, Ns, N1, N2, w);
+        INF3DP_LAUNCH_CHECK("isect_elect_kernel");
+    }
+    {   // cells without a winner (all of them when there are no voxels) get the default outputs here
+        const long long tiles = (long long)((Ns + kCellTileS - 1) / kCellTileS) * N1 * ((N2 + kCellTile2 - 1) / kCellTile2);
+        const long long blocks = std::min<long long>(tiles, (long long)num_sms() * 32);
+        isect_cell_kernel<GRID><<<(unsigned)blocks, 256, 0, st>>>(src, s_iso, a_iso, b_iso, Dx, Ns, N1, N2, tiles, w, mask, idx, pts);
+        INF3DP_LAUNCH_CHECK("isect_cell_kernel");
+    }
+    return INF3DP_OK;
 }
 
 }  // namespace
@@ -317,44 +432,24 @@ int inf3dp_fields_intersection(const float* sf, const float* af, const float* bf
                                const float* a_iso, const float* b_iso, const float* centers, int Dx, int Dy, int Dz,
                                int Ns, int N1, int N2, uint8_t* mask, int16_t* idx, float* pts, void* ws,
                                size_t ws_bytes, inf3dp_stream_t stream) {
-    INF3DP_CHECK_ARG(Dx >= 0 && Dy >= 0 && Dz >= 0 && Ns >= 0 && N1 >= 0 && N2 >= 0, "fields_intersection: negative size");
-    const long long voxels = (long long)Dx * Dy * Dz, cells = (long long)Ns * N1 * N2;
-    if (cells == 0) return INF3DP_OK;
-    INF3DP_CHECK_ARG(voxels < 0x7fffffffll, "fields_intersection: %lld voxels exceed the int32 voxel index", voxels);
-    INF3DP_CHECK_ARG(Ns <= 32767 && N1 <= 32767 && N2 <= 32767,
-                     "fields_intersection: isovalue counts must fit the int16 index output (intersection.cu:247)");
-    INF3DP_CHECK_ARG(mask && idx && pts && ws && s_iso && a_iso && b_iso, "fields_intersection: null pointer");
-    INF3DP_CHECK_ARG(voxels == 0 || (sf && af && bf && centers), "fields_intersection: null pointer");
-    INF3DP_CHECK_ARG(((reinterpret_cast<uintptr_t>(sf) | reinterpret_cast<uintptr_t>(af) | reinterpret_cast<uintptr_t>(bf) |
-                       reinterpret_cast<uintptr_t>(pts) | reinterpret_cast<uintptr_t>(idx) |
-                       reinterpret_cast<uintptr_t>(mask)) & 15) == 0,
+    const long long voxels = (long long)Dx * Dy * Dz;
+    INF3DP_CHECK_ARG(Dx >= 0 && Dy >= 0 && Dz >= 0, "fields_intersection: negative size");
+    INF3DP_CHECK_ARG(voxels == 0 || centers, "fields_intersection: null pointer");
+    INF3DP_CHECK_ARG(((reinterpret_cast<uintptr_t>(sf) | reinterpret_cast<uintptr_t>(af) | reinterpret_cast<uintptr_t>(bf)) & 15) == 0,
                      "fields_intersection: field and output pointers must be 16-byte aligned");
-    IsectWs w = carve_isect(ws, voxels > 0 ? voxels : 1, cells, Ns, N1, N2);
-    if (ws_bytes < w.total_bytes) {
-        set_error("fields_intersection: workspace has %zu bytes, need %zu", ws_bytes, w.total_bytes);
-        return INF3DP_EWORKSPACE;
-    }
-    cudaStream_t st = (cudaStream_t)stream;
-    isect_prep_kernel<<<1, 1024, 0, st>>>(s_iso, a_iso, b_iso, Ns, N1, N2, w);
-    INF3DP_LAUNCH_CHECK("isect_prep_kernel");
-    const long long quads = (cells + 3) / 4;
-    isect_init_kernel<<<(unsigned)((quads + 255) / 256), 256, 0, st>>>(cells, w.winner);
-    INF3DP_LAUNCH_CHECK("isect_init_kernel");
-    if (voxels > 0) {
-        const size_t tab_smem = (Ns + N1 + N2) <= kMaxTableEntries ? (size_t)(Ns + N1 + N2) * 8 : 0;
-        if (tab_smem > 40 * 1024) {
-            INF3DP_CUDA(cudaFuncSetAttribute(isect_elect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tab_smem));
-        }
-        isect_elect_kernel<<<(unsigned)std::min<long long>((voxels + 255) / 256, (long long)num_sms() * 16), 256, tab_smem, st>>>(sf, af, bf, voxels, Ns, N1, N2, w);
-        INF3DP_LAUNCH_CHECK("isect_elect_kernel");
-    }
-    {   // cells without a winner (all of them when there are no voxels) get the default outputs here
-        const long long tiles = (long long)((Ns + kCellTileS - 1) / kCellTileS) * N1 * ((N2 + kCellTile2 - 1) / kCellTile2);
-        const long long blocks = std::min<long long>(tiles, (long long)num_sms() * 32);
-        isect_cell_kernel<<<(unsigned)blocks, 256, 0, st>>>(sf, af, bf, centers, s_iso, a_iso, b_iso, Dx, Ns, N1, N2, tiles, w, mask, idx, pts);
-        INF3DP_LAUNCH_CHECK("isect_cell_kernel");
-    }
-    return INF3DP_OK;
+    FieldSrc src{sf, af, bf, centers, Dy, Dz, 0, 0, 0.f};
+    return isect_run<false>(src, s_iso, a_iso, b_iso, Dx, Dy, Dz, Ns, N1, N2, mask, idx, pts, ws, ws_bytes, stream);
+}
+
+int inf3dp_fields_intersection_grid(const float* sg, const float* ag, const float* bg, const float* s_iso,
+                                    const float* a_iso, const float* b_iso, int Gx, int Gy, int Gz, int Ns, int N1,
+                                    int N2, uint8_t* mask, int16_t* idx, float* pts, void* ws, size_t ws_bytes,
+                                    inf3dp_stream_t stream) {
+    INF3DP_CHECK_ARG(Gx >= 1 && Gy >= 1 && Gz >= 1, "fields_intersection_grid: grids need at least one sample per axis");
+    const int Dx = Gx - 1, Dy = Gy - 1, Dz = Gz - 1;
+    FieldSrc src{sg, ag, bg, nullptr, Dy, Dz, (long long)Gy * Gz, (long long)Gz,
+                 Gx > 1 ? (float)(2.0 / (double)(Gx - 1)) : 0.f};
+    return isect_run<true>(src, s_iso, a_iso, b_iso, Dx, Dy, Dz, Ns, N1, N2, mask, idx, pts, ws, ws_bytes, stream);
 }
 
 }  // extern "C"

@@ -11,6 +11,8 @@ from .diffops import (gradient, hessian, hessian3d, jacobian, divergence, laplac
                       min_max_curvs_and_vectors, unit_normals)
 from .query import field_querying, field_query_with_grads, HostPipeline
 from .projection import batch_isosurface_projection, iter_project_contours_batch
+from .volume import (grid_queries, grid_field, get_grid_fields, marching_cubes, sdf_to_mesh, gen_iso_layers,
+                     get_fields_intersection_from_grids)
 from .collision import (CollTVSDF, collision_evaluation, tvsdf_collision_forward, quat_collision_sweep,
                         transform_nozzle_pcd_with_quaternion)
 
@@ -33,5 +35,6 @@ __all__ = [
     "divergence", "laplace", "principal_curvatures", "min_max_curvs_and_vectors", "unit_normals", "field_querying",
     "field_query_with_grads", "HostPipeline", "patch_reference", "batch_isosurface_projection",
     "iter_project_contours_batch", "CollTVSDF", "collision_evaluation", "tvsdf_collision_forward", "quat_collision_sweep",
-    "transform_nozzle_pcd_with_quaternion",
+    "transform_nozzle_pcd_with_quaternion", "grid_queries", "grid_field", "get_grid_fields", "marching_cubes",
+    "sdf_to_mesh", "gen_iso_layers", "get_fields_intersection_from_grids",
 ]
