@@ -277,6 +277,61 @@ def bench_collision(sdf_net, dev, n_waypoints=4_194_304, m_nozzle=64):
             "api": "inf3dp.quat_collision_sweep (quaternion field + level_collision.CollTVSDF forward, device resident)"}
 
 
+def bench_volume(net, dev, peaks):
+    """fused grid sweep (no coordinate tensor), marching cubes on the resulting 512^3 volume, and the
+    three-field intersection fed by 256^3 sample grids (no corner expansion)."""
+    import torch
+    import inf3dp
+
+    def timeit(fn, reps):
+        fn()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            out = fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / reps, out
+
+    N = GRID_N
+    ms_sweep, sdf = timeit(lambda: inf3dp.grid_field(net, N, chunk=1 << 23), 1)
+    level = float(sdf.flatten()[:: 4099].median())     # the random-init SDF never crosses 0: take a level that exists
+    h = 2.0 / (N - 1)
+    ms_mc, (v, f, nrm, val) = timeit(lambda: inf3dp.marching_cubes(sdf, level, (h, h, h)), 3)
+    mc_bytes = 4 * N ** 3 + v.numel() * 4 + f.numel() * 4 + nrm.numel() * 4 + val.numel() * 4
+    nv, nf = int(v.shape[0]), int(f.shape[0])
+    del sdf, v, f, nrm, val
+    G = 256
+    g = torch.stack(torch.meshgrid(*[torch.linspace(-1, 1, G, device=dev)] * 3, indexing="ij"), -1)
+    grids = [(g[..., 2] + 0.1 * torch.sin(3 * g[..., 0])).contiguous(), (g[..., 0] + 0.2 * g[..., 1] ** 2).contiguous(),
+             (g[..., 1] - 0.15 * g[..., 2] * g[..., 0]).contiguous()]
+    del g
+    Ns, N1, N2 = 500, 128, 128
+    isos = [torch.linspace(-0.9, 0.9, Ns, device=dev), torch.linspace(-0.8, 0.8, N1, device=dev),
+            torch.linspace(-0.8, 0.8, N2, device=dev)]
+    ms_is, out = timeit(lambda: inf3dp.get_fields_intersection_from_grids(*grids, *isos, sync=False), 3)
+    cells = Ns * N1 * N2
+    is_bytes = 12 * G ** 3 + 4 * (Ns + N1 + N2) + 19 * cells
+    return {
+        "grid_sweep": {"metric": "siren_value_points_per_s", "value": N ** 3 / (ms_sweep / 1e3), "unit": "points/s",
+                       "ms": ms_sweep, "grid": N, "api": "inf3dp.grid_field (device query-grid generator + fused value launches, "
+                       "no [N^3,3] coordinate tensor)"},
+        "marching_cubes": {"metric": "marching_cubes_ms", "ms_per_call": ms_mc, "grid": N, "level": level, "vertices": nv,
+                           "triangles": nf, "launches_per_call": 4,
+                           "roofline": {"bound": "hbm", "achieved": mc_bytes / (ms_mc / 1e3) / 1e9, "peak": peaks["hbm"],
+                                        "unit": "GB/s", "frac": mc_bytes / (ms_mc / 1e3) / 1e9 / peaks["hbm"],
+                                        "bytes_algorithmic": mc_bytes, "traffic": None,
+                                        "note": "count kernel is instruction bound (profiles/r1c_volume_ncu_summary.md)"}},
+        "intersection_on_grids": {"metric": "intersection_ms", "ms_per_call": ms_is, "grid": G, "isovalues": [Ns, N1, N2],
+                                  "cells_hit": int(out[0].sum()), "launches_per_call": 4,
+                                  "roofline": {"bound": "hbm", "achieved": is_bytes / (ms_is / 1e3) / 1e9, "peak": peaks["hbm"],
+                                               "unit": "GB/s", "frac": is_bytes / (ms_is / 1e3) / 1e9 / peaks["hbm"],
+                                               "bytes_algorithmic": is_bytes, "traffic": None,
+                                               "note": "replaces 3 x 8x corner expansion (1.6 GB) + centre tensor + ext call"}},
+    }
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -386,6 +441,7 @@ def run_ours(args):
         iso = bench_isocontours(dev, peaks)
         hess = bench_hessian_sweep(net, dev, peaks)
         coll = bench_collision(net, dev)
+        vol = bench_volume(net, dev, peaks)
         cores = os.cpu_count() or 1
         cpu_base = None
         if world == 1:   # reported baseline: rank 0 at N=1 only (torchrun pins OMP threads to 1 for N>1)
@@ -423,6 +479,7 @@ def run_ours(args):
             "isocontour": iso,
             "hessian_sweep": hess,
             "collision_sweep": coll,
+            "volume": vol,
             "clocks": clocks,
             "torch": torch.__version__,
         }

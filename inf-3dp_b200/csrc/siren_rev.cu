@@ -217,9 +217,9 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
 #pragma unroll
                     for (int r = 0; r < 4; ++r) {
                         long long t0 = dbg ? clock64() : 0;
-                        mbar_wait(bar(C::kBarAReady + r), aphase);
+                        mbar_wait<true>(bar(C::kBarAReady + r), aphase);
                         long long t1 = dbg ? clock64() : 0;
-                        mbar_wait(bar(C::kBarWFull + stage), wphase);
+                        mbar_wait<true>(bar(C::kBarWFull + stage), wphase);
                         if (dbg) {
                             wait_a += (unsigned long long)(t1 - t0);
                             wait_w += (unsigned long long)(clock64() - t1);
@@ -488,31 +488,48 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
             }
         }
         } else {
-        for (int it = 0; it < my_units; ++it) {
+        // The unit boundary is fused: the first tile's layer 0 is a prologue, every later tile's layer 0 is produced INSIDE
+        // the rounds of the previous tile's last epilogue (GEMM 5), slice by slice over the accumulator columns that were
+        // just read -- so the MMAs of the next tile's first GEMM start after one epilogue round, like any other GEMM,
+        // instead of after the whole input-layer epilogue, the output reduction and a fresh layer 0.
+        auto load_point = [&](int it, int64_t& pt, bool& pvalid, float& px, float& py, float& pz) {
             const int64_t tile = (unit0 + (int64_t)it * unit_stride) * CTAS + rank;
-            const int64_t pt = tile * 128 + row;
-            const bool pvalid = pt < n;
-            float px = 0.f, py = 0.f, pz = 0.f;
+            pt = tile * 128 + row;
+            pvalid = it < my_units && pt < n;
+            px = py = pz = 0.f;
             if (pvalid) { px = x[3 * pt]; py = x[3 * pt + 1]; pz = x[3 * pt + 2]; }
-
-            // ---- layer 0 (FP32): a0 = sin(W0' x + b0')  -> region P -------------------------------------------------
+        };
+        auto layer0_slice = [&](int m, float qx, float qy, float qz, uint32_t* o) {   // a0 = sin(W0' x + b0'), FP32
+#pragma unroll
+            for (int i = 0; i < 16; i += 2) {
+                float r2[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const float4 w = s_w0[16 * m + i + u];
+                    r2[u] = sin_layer0(fmaf(w.z, qz, fmaf(w.y, qy, fmaf(w.x, qx, w.w))));
+                }
+                split_pack<true>(r2[0], r2[1], o[i >> 1], o[8 + (i >> 1)]);
+            }
+        };
+        int64_t pt;
+        bool pvalid;
+        float px, py, pz;
+        load_point(0, pt, pvalid, px, py, pz);
+        if (my_units > 0) {
 #pragma unroll 1
             for (int mi = 0; mi < 4; ++mi) {
                 const int m = grp + 4 * mi;
                 uint32_t o[16];
-#pragma unroll
-                for (int i = 0; i < 16; i += 2) {
-                    float r2[2];
-#pragma unroll
-                    for (int u = 0; u < 2; ++u) {
-                        const float4 w = s_w0[16 * m + i + u];
-                        r2[u] = sin_layer0(fmaf(w.z, pz, fmaf(w.y, py, fmaf(w.x, px, w.w))));
-                    }
-                    split_pack<true>(r2[0], r2[1], o[i >> 1], o[8 + (i >> 1)]);
-                }
+                layer0_slice(m, px, py, pz, o);
                 TC_ST16(regionP + lane_off + 16u * (uint32_t)m, o);
                 publish(mi);
             }
+        }
+        for (int it = 0; it < my_units; ++it) {
+            int64_t npt = 0;                       // the next tile's point (prefetched while this tile's GEMMs run)
+            bool nvalid = false;
+            float nx = 0.f, ny = 0.f, nz = 0.f;
+            const bool has_next = it + 1 < my_units;
 
             float acc_y = 0.f, gx = 0.f, gy = 0.f, gz = 0.f;
 #pragma unroll
@@ -520,6 +537,7 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
                 const uint32_t regD = (g & 1) ? regionP : regionQ;
                 const float inv = s_misc[g < 3 ? g : 5 - g];              // 1/S of the layer this GEMM multiplies by
                 float4 cs[4];                                             // stashed cosines of the current slice
+                if (g == 3) load_point(it + 1, npt, nvalid, nx, ny, nz);  // global-load latency hidden behind two GEMMs
                 if (g == 3 || g == 4) {                                   // issue the first stash read under the wait
                     const float4* sp = my_stash + (size_t)(((4 - g) * 16 + grp) * 4) * 128;
 #pragma unroll
@@ -603,8 +621,10 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
                             gy = fmaf(g0, w.y, gy);
                             gz = fmaf(g0, w.z, gz);
                         }
+                        // these accumulator columns (region P, slice m) are dead now: the next tile's layer 0 goes there
+                        if (has_next) layer0_slice(m, nx, ny, nz, o);
                     }
-                    if (g < 5) {
+                    if (g < 5 || has_next) {
                         TC_ST16(addr, o);
                         publish(mi);
                     }
@@ -629,9 +649,10 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
                 J[3 * pt + 1] = r4[2] * inv_g;
                 J[3 * pt + 2] = r4[3] * inv_g;
             }
-            // Hazards into the next unit: region P (next layer-0 target) holds the last D, which this warp has finished
-            // reading (tcgen05.wait::ld above); s_part is rewritten only after six more d_full phases, which need every
-            // epilogue warp (including the readers) to have published its next layer-0 slices.
+            // Hazards into the next unit: the next tile's layer 0 overwrote exactly the accumulator slices this warp had
+            // finished reading (tcgen05.wait::ld before the math of each round); s_part is rewritten only after six more
+            // d_full phases, which need every epilogue warp (including the readers above) to have passed this point.
+            pt = npt; pvalid = nvalid; px = nx; py = ny; pz = nz;
         }
         }
         if (dbg && blockIdx.x == 0 && lane == 0) dbg[8 + warp] = wait_d;

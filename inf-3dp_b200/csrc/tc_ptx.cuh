@@ -30,11 +30,15 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     return ok != 0;
 }
 // Wait with a watchdog: a protocol bug traps (launch failure) instead of hanging the device.
+// HOT = true: no back-off sleep (the hand-over waits on the critical path: mbarrier.try_wait already suspends the
+// thread for a hardware time slice, a __nanosleep on top only delays the wake-up).
+template <bool HOT = false>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > 16u) __nanosleep(40);
+        ++spins;
+        if (!HOT && spins > 16u) __nanosleep(40);
         if (spins > (1u << 24)) {  // >~ 1 s: a protocol bug, not a slow kernel
             printf("inf3dp siren_tc: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x,
                    threadIdx.x, bar, parity);
@@ -50,9 +54,9 @@ __device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity, in
 }
 // Developer instrumentation (INF3DP_TC_DEBUG=1): cycles spent blocked in a wait, accumulated per role.
 __device__ __forceinline__ void mbar_wait_timed(uint32_t bar, uint32_t parity, unsigned long long* acc) {
-    if (acc == nullptr) { mbar_wait(bar, parity); return; }
+    if (acc == nullptr) { mbar_wait<true>(bar, parity); return; }
     const long long t0 = clock64();
-    mbar_wait(bar, parity);
+    mbar_wait<true>(bar, parity);
     *acc += (unsigned long long)(clock64() - t0);
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {

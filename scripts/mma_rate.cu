@@ -118,7 +118,7 @@ void run(int variant, int n_mma, int grid) {
 int main() {
     const int n = 960;
     for (int grid : {148}) {
-        for (int v : {0, 16, 48}) {
+        for (int v : {0, 2, 16, 18, 48, 50}) {
             run<1>(v, n, grid);
             run<2>(v, n, grid);
         }
