@@ -34,6 +34,11 @@ namespace {
 constexpr int kFaceThreads = 256;
 constexpr unsigned long long kEmptyKey = 0xFFFFFFFFFFFFFFFFull;
 
+// big walk tier (multi-million-face meshes): list capacities per isovalue, kept in the workspace
+constexpr int kBigMaxLoops = 2048, kBigMaxPaths = 1024;
+constexpr int kWalkListInts = 7 * kBigMaxLoops + 3 * kBigMaxPaths;
+constexpr int kWalkBigMinFaces = 1500000;   // pools at least this large carry the lists (see launch_walk)
+
 struct ContourWs {
     // header (device): [0] overflow flag, [1] total segments, [2] hash slots in use (pow2), [3] segment capacity
     int* hdr;
@@ -51,6 +56,7 @@ struct ContourWs {
     unsigned char* used; // [cap]
     unsigned long long* hkeys;  // [hcap]
     int* hvals;          // [hcap][2]
+    int* walk_lists;     // [K][kWalkListInts] piece / chain lists of the big walk tier (null for small pools)
     int cap;
     int hcap;
     int defer;           // 1: the walk records the row order (endpoint ids) in seg_order, rows are written by the scatter kernel
@@ -96,6 +102,7 @@ ContourWs carve(void* base, int K, int cap) {
     w.used = (unsigned char*)(b + take((size_t)w.cap));
     w.hkeys = (unsigned long long*)(b + take((size_t)w.hcap * 8));
     w.hvals = (int*)(b + take((size_t)w.hcap * 8));
+    w.walk_lists = w.cap >= kWalkBigMinFaces ? (int*)(b + take((size_t)K * kWalkListInts * 4)) : nullptr;
     w.total_bytes = o;
     return w;
 }
@@ -366,9 +373,18 @@ constexpr int kWalkThreads = 512;
 // K <= 296 isovalues are one wave).  Larger isovalues walk in the workspace.
 constexpr int kWalkSmemSegs = 5120;
 constexpr int kWalkSmemBytes = kWalkSmemSegs * 20;
-constexpr int kRankPerThread = 2 * kWalkSmemSegs / kWalkThreads;   // traversal states per thread in the ranked path (24)
-constexpr int kRankMaxLoops = 320;   // contour pieces (closed loops + pieces of open chains) per isovalue
-constexpr int kRankMaxPaths = 32;    // open chains per isovalue
+// Second tier for multi-million-face meshes (F = 4 M, K = 200: up to ~10 k segments per isovalue): 210 KB, one CTA per SM.
+constexpr int kWalkBigSegs = 11264;
+constexpr int kWalkBigBytes = kWalkBigSegs * 20;
+// list capacities per isovalue: contour pieces (closed loops + pieces of open chains) and open chains.  The small tier
+// keeps its lists in shared memory; the big tier keeps them in the workspace (L1/L2 resident, touched by a few threads):
+// at F = 4 M a few isovalues run along mesh edges and break into hundreds of pieces (the reference's 1e-6 merge radius),
+// and their serial fallback (~2 ms each) would otherwise be the critical path of the whole call.
+template <int CAP> struct RankCaps {
+    static constexpr bool kGlobal = CAP > 5120;
+    static constexpr int kLoops = kGlobal ? kBigMaxLoops : 320;
+    static constexpr int kPaths = kGlobal ? kBigMaxPaths : 32;
+};
 
 // Where isovalue k's row stream goes, and how many rows fit: the dense [K, F, 3] contract of the reference
 // (isocontours.cu:230-236), or the compact layout (2 S_k rows at 2 * seg_offset[k]; rows used = S_k + C_k <= 2 S_k).
@@ -533,22 +549,34 @@ __device__ __forceinline__ void walk_isovalue(int S, int off, int nF, int k, con
 // direction writes its own output row: rank 0 -> the seed's p1, rank r >= 1 -> the exit endpoint of the r-th segment
 // (isocontours.cu:143-203), then the (-1e9) separator row (:135-140, :205-210).
 // Returns false (nothing written) when a list capacity is exceeded: the caller then walks the isovalue serially.
+template <int CAP>
 __device__ bool walk_ranked(int S, int off, int nF, int k, const ContourWs& w, unsigned char* smem,
                             float* __restrict__ merged, int* __restrict__ nums) {
     unsigned short* J = reinterpret_cast<unsigned short*>(smem);                 // [2S] jump pointers
-    unsigned short* D = J + 2 * kWalkSmemSegs;                                   // [2S] distances
-    int* V = reinterpret_cast<int*>(D + 2 * kWalkSmemSegs);                      // [2S] keys (closed) / dead-end info (open)
-    unsigned short* NX = reinterpret_cast<unsigned short*>(V + 2 * kWalkSmemSegs);  // [2S] next(e); later P | Q
+    unsigned short* D = J + 2 * CAP;                                   // [2S] distances
+    int* V = reinterpret_cast<int*>(D + 2 * CAP);                      // [2S] keys (closed) / dead-end info (open)
+    unsigned short* NX = reinterpret_cast<unsigned short*>(V + 2 * CAP);  // [2S] next(e); later P | Q
     unsigned short* P = NX;                                                      // [S] state at a chain position
-    unsigned short* Q = NX + kWalkSmemSegs;                                      // [S] piece of a chain position
+    unsigned short* Q = NX + CAP;                                      // [S] piece of a chain position
     constexpr unsigned short kNone = 0xFFFFu;
+    constexpr int kMaxLoops = RankCaps<CAP>::kLoops, kMaxPaths = RankCaps<CAP>::kPaths;
+    constexpr int kRPT = 2 * CAP / kWalkThreads;   // traversal states per thread (20 / 42)
+    static_assert(2 * CAP < 32768, "state ids are packed into 15 bits of V");
     __shared__ int s_nloops, s_npaths, s_slot;
-    __shared__ int s_lface[kRankMaxLoops], s_llen[kRankMaxLoops];   // piece: seed face, length (discovery order)
-    __shared__ int s_linfo[kRankMaxLoops];                          // open piece: seed position << 1 | reverse flag
-    __shared__ int s_lbase[kRankMaxLoops];                          // piece: first output row
-    __shared__ int s_sface[kRankMaxLoops], s_slen[kRankMaxLoops], s_sbase[kRankMaxLoops];   // sorted by seed face
-    __shared__ int s_pterm[kRankMaxPaths], s_plen[kRankMaxPaths], s_pbase[kRankMaxPaths];   // chain: dead end, length, P offset
-    __shared__ unsigned long long s_cmin[kWalkSmemSegs / 32];   // per 32 chain positions: min (face << 32 | position)
+    constexpr bool kGlobalLists = RankCaps<CAP>::kGlobal;
+    __shared__ int s_lists[kGlobalLists ? 1 : 7 * kMaxLoops + 3 * kMaxPaths];
+    int* const lists = kGlobalLists ? w.walk_lists + (size_t)k * kWalkListInts : s_lists;
+    int* const s_lface = lists;                      // piece: seed face (discovery order)
+    int* const s_llen = lists + kMaxLoops;           //        length
+    int* const s_linfo = lists + 2 * kMaxLoops;      // open piece: seed position << 1 | reverse flag
+    int* const s_lbase = lists + 3 * kMaxLoops;      // piece: first output row
+    int* const s_sface = lists + 4 * kMaxLoops;      // sorted by seed face
+    int* const s_slen = lists + 5 * kMaxLoops;
+    int* const s_sbase = lists + 6 * kMaxLoops;
+    int* const s_pterm = lists + 7 * kMaxLoops;      // chain: dead end
+    int* const s_plen = s_pterm + kMaxPaths;         //        length
+    int* const s_pbase = s_pterm + 2 * kMaxPaths;    //        P offset
+    __shared__ unsigned long long s_cmin[CAP / 32];   // per 32 chain positions: min (face << 32 | position)
     const int tid = threadIdx.x;
     const int n = 2 * S;
     const unsigned long long keep = keep_policy();
@@ -570,10 +598,10 @@ __device__ bool walk_ranked(int S, int off, int nF, int k, const ContourWs& w, u
     auto doubling = [&](auto mode_tag) {
         constexpr int MODE = decltype(mode_tag)::value;
         for (int step = 1; step < S; step <<= 1) {
-            unsigned int njd[kRankPerThread];   // new jump pointer (low half) and distance (high half)
-            int nv[kRankPerThread];
+            unsigned int njd[kRPT];   // new jump pointer (low half) and distance (high half)
+            int nv[kRPT];
 #pragma unroll
-            for (int q = 0; q < kRankPerThread; ++q) {
+            for (int q = 0; q < kRPT; ++q) {
                 if (q * kWalkThreads >= n) break;   // uniform
                 const int e = tid + q * kWalkThreads;
                 if (e < n) {
@@ -595,7 +623,7 @@ __device__ bool walk_ranked(int S, int off, int nF, int k, const ContourWs& w, u
             }
             __syncthreads();
 #pragma unroll
-            for (int q = 0; q < kRankPerThread; ++q) {
+            for (int q = 0; q < kRPT; ++q) {
                 if (q * kWalkThreads >= n) break;   // uniform
                 const int e = tid + q * kWalkThreads;
                 if (e < n) {
@@ -618,9 +646,9 @@ __device__ bool walk_ranked(int S, int off, int nF, int k, const ContourWs& w, u
         doubling(std::integral_constant<int, 0>{});
         // open state <=> its jump target is a dead end.  Keep (dead end, distance) in V (sign bit set) and the face id
         // in the now free (J, D) pair of the state.
-        int vnew[kRankPerThread];
+        int vnew[kRPT];
 #pragma unroll
-        for (int q = 0; q < kRankPerThread; ++q) {
+        for (int q = 0; q < kRPT; ++q) {
             if (q * kWalkThreads >= n) break;
             const int e = tid + q * kWalkThreads;
             if (e < n) {
@@ -630,7 +658,7 @@ __device__ bool walk_ranked(int S, int off, int nF, int k, const ContourWs& w, u
         }
         __syncthreads();
 #pragma unroll
-        for (int q = 0; q < kRankPerThread; ++q) {
+        for (int q = 0; q < kRPT; ++q) {
             if (q * kWalkThreads >= n) break;
             const int e = tid + q * kWalkThreads;
             if (e < n) {
@@ -652,7 +680,7 @@ __device__ bool walk_ranked(int S, int off, int nF, int k, const ContourWs& w, u
         const int e = 2 * i;
         if (V[e] >= 0 && D[e] == 0 && (V[e] & 1) == 0) {
             const int slot = atomicAdd(&s_nloops, 1);
-            if (slot < kRankMaxLoops) {
+            if (slot < kMaxLoops) {
                 s_lface[slot] = V[e] >> 1;
                 s_llen[slot] = (int)D[NX[e]] + 1;    // the state after the seed is length - 1 steps behind it
                 s_linfo[slot] = -1;
@@ -660,21 +688,21 @@ __device__ bool walk_ranked(int S, int off, int nF, int k, const ContourWs& w, u
         }
     }
     __syncthreads();
-    if (s_nloops > kRankMaxLoops) return false;
+    if (s_nloops > kMaxLoops) return false;
 
     if (mixed) {
         // ---- open chains: canonical direction = the one whose dead end has the smaller state id ------------------------
-        auto dead_end = [&](int e) { return (int)(((unsigned int)V[e] >> 16) & 0x3fffu); };
+        auto dead_end = [&](int e) { return (int)(((unsigned int)V[e] >> 16) & 0x7fffu); };
         auto dist_end = [&](int e) { return (int)((unsigned int)V[e] & 0xffffu); };
         for (int e = tid; e < n; e += kWalkThreads) {
             if (V[e] < 0 && NX[e] == kNone && e < dead_end(e ^ 1)) {   // e is the dead end of a canonical direction
                 const int slot = atomicAdd(&s_npaths, 1);
-                if (slot < kRankMaxPaths) { s_pterm[slot] = e; s_plen[slot] = dist_end(e ^ 1) + 1; }
+                if (slot < kMaxPaths) { s_pterm[slot] = e; s_plen[slot] = dist_end(e ^ 1) + 1; }
             }
         }
         __syncthreads();
         const int npaths = s_npaths;
-        if (npaths > kRankMaxPaths) return false;
+        if (npaths > kMaxPaths) return false;
         if (tid == 0) { int run = 0; for (int c = 0; c < npaths; ++c) { s_pbase[c] = run; run += s_plen[c]; } }
         __syncthreads();   // NX is dead from here on: its storage becomes P | Q
         for (int e = tid; e < n; e += kWalkThreads) {
@@ -691,15 +719,15 @@ __device__ bool walk_ranked(int S, int off, int nF, int k, const ContourWs& w, u
         int* facepos = reinterpret_cast<int*>(J);
         {
             const int total = s_pbase[npaths - 1] + s_plen[npaths - 1];
-            int fr[(kWalkSmemSegs + kWalkThreads - 1) / kWalkThreads];
+            int fr[(CAP + kWalkThreads - 1) / kWalkThreads];
 #pragma unroll
-            for (int q = 0; q < (kWalkSmemSegs + kWalkThreads - 1) / kWalkThreads; ++q) {
+            for (int q = 0; q < (CAP + kWalkThreads - 1) / kWalkThreads; ++q) {
                 const int g = tid + q * kWalkThreads;
                 if (g < total) { const int e = P[g]; fr[q] = (int)((unsigned int)J[e] | ((unsigned int)D[e] << 16)); }
             }
             __syncthreads();
 #pragma unroll
-            for (int q = 0; q < (kWalkSmemSegs + kWalkThreads - 1) / kWalkThreads; ++q) {
+            for (int q = 0; q < (CAP + kWalkThreads - 1) / kWalkThreads; ++q) {
                 const int g = tid + q * kWalkThreads;
                 if (g < total) facepos[g] = fr[q];
             }
@@ -752,7 +780,7 @@ __device__ bool walk_ranked(int S, int off, int nF, int k, const ContourWs& w, u
                 int slot = 0;
                 if (lane == 0) slot = atomicAdd(&s_nloops, 1);
                 slot = __shfl_sync(0xffffffffu, slot, 0);
-                if (slot >= kRankMaxLoops) { s_slot = 1; break; }
+                if (slot >= kMaxLoops) { s_slot = 1; break; }
                 if (lane == 0) {
                     s_lface[slot] = (int)fmin;
                     s_llen[slot] = a1 - a0 + 1;
@@ -831,8 +859,12 @@ __device__ bool walk_ranked(int S, int off, int nF, int k, const ContourWs& w, u
     return true;
 }
 
-__global__ void __launch_bounds__(kWalkThreads, 2)
-contour_walk_kernel(int nF, ContourWs w, float* __restrict__ merged, int* __restrict__ nums) {
+// Two tiers of the shared-memory walk: CAP = kWalkSmemSegs (100 KB, two CTAs per SM) and CAP = kWalkBigSegs (210 KB, one
+// CTA per SM) for the isovalues of multi-million-face meshes; a launch of tier T handles exactly the isovalues whose
+// segment count falls into its range and leaves the others to the other launch.
+template <int CAP, int MIN_CTAS, bool BIG>
+__global__ void __launch_bounds__(kWalkThreads, MIN_CTAS)
+contour_walk_kernel(int nF, int two_tiers, ContourWs w, float* __restrict__ merged, int* __restrict__ nums) {
     extern __shared__ int s_dyn[];
     const int k = blockIdx.x;
     const long long t_begin = clock64();
@@ -840,6 +872,10 @@ contour_walk_kernel(int nF, ContourWs w, float* __restrict__ merged, int* __rest
     const bool overflow = w.hdr[0] != 0;
     const int S = overflow ? 0 : w.seg_count[k];
     const int off = w.seg_offset[k];
+    if (BIG ? (S <= kWalkSmemSegs || S > kWalkBigSegs) : (two_tiers && S > kWalkSmemSegs && S <= kWalkBigSegs)) {
+        stamp.slot = &w.hdr[15];   // not this tier's isovalue: leave its time stamp alone
+        return;
+    }
     if (S == 0) {
         if (threadIdx.x == 0) { nums[k] = 0; w.rows_used[k] = 0; }
         return;
@@ -847,20 +883,41 @@ contour_walk_kernel(int nF, ContourWs w, float* __restrict__ merged, int* __rest
     // Working set of the chain walk: partner links (local endpoint ids), the row order being recorded and the
     // per-segment consumed flags.  In shared memory when the isovalue fits (no global traffic on the chain, which
     // matters because the zero fill saturates HBM concurrently), in the workspace otherwise.
-    if (S <= kWalkSmemSegs) {
-        if (walk_ranked(S, off, nF, k, w, reinterpret_cast<unsigned char*>(s_dyn), merged, nums)) return;
+    if (S <= CAP) {
+        if (walk_ranked<CAP>(S, off, nF, k, w, reinterpret_cast<unsigned char*>(s_dyn), merged, nums)) return;
         __syncthreads();
         if (threadIdx.x == 0) atomicAdd(&w.hdr[8], 1);   // statistics: isovalues walked serially
         unsigned short* nx = reinterpret_cast<unsigned short*>(s_dyn);
-        unsigned short* order = nx + 2 * kWalkSmemSegs;
-        int* face = reinterpret_cast<int*>(order + 2 * kWalkSmemSegs);
-        unsigned char* used = reinterpret_cast<unsigned char*>(face + kWalkSmemSegs);
+        unsigned short* order = nx + 2 * CAP;
+        int* face = reinterpret_cast<int*>(order + 2 * CAP);
+        unsigned char* used = reinterpret_cast<unsigned char*>(face + CAP);
         walk_isovalue<unsigned short, unsigned char>(S, off, nF, k, w, nx, order, used, face, nullptr, merged, nums);
     } else {
         // the hash-slot array is dead after `link`: reuse it as int flags
+        if (threadIdx.x == 0) atomicAdd(&w.hdr[8], 1);
         walk_isovalue<int, int>(S, off, nF, k, w, w.seg_link + 2ll * off, w.seg_order + 2ll * off, w.seg_slot + 2ll * off,
                                 nullptr, nullptr, merged, nums);
     }
+}
+
+// Both tiers of the walk.  A CTA of the big tier needs a whole SM (210 KB of shared memory, 58 k registers): while the
+// zero fill of the dense contract occupies the SMs its CTAs -- even the ones that exit at once -- are only placed as the
+// fill drains.  It is therefore launched only for meshes large enough to have isovalues beyond the small tier
+// (S_k grows like sqrt(F): 4.6 k at F = 1 M, 9.4 k at F = 4 M on the closed bench mesh); below that threshold an isovalue
+// with more than kWalkSmemSegs segments is walked serially, as before.
+inline cudaError_t launch_walk(int nF, int K, const ContourWs& w, float* out, int* nums, cudaStream_t st) {
+    auto small = contour_walk_kernel<kWalkSmemSegs, 2, false>;
+    auto big = contour_walk_kernel<kWalkBigSegs, 1, true>;
+    const bool use_big = nF >= kWalkBigMinFaces && w.walk_lists != nullptr;
+    cudaError_t e = cudaFuncSetAttribute(small, cudaFuncAttributeMaxDynamicSharedMemorySize, kWalkSmemBytes);
+    if (e != cudaSuccess) return e;
+    small<<<K, kWalkThreads, kWalkSmemBytes, st>>>(nF, use_big ? 1 : 0, w, out, nums);
+    if (use_big) {
+        e = cudaFuncSetAttribute(big, cudaFuncAttributeMaxDynamicSharedMemorySize, kWalkBigBytes);
+        if (e != cudaSuccess) return e;
+        big<<<K, kWalkThreads, kWalkBigBytes, st>>>(nF, 1, w, out, nums);
+    }
+    return cudaGetLastError();
 }
 
 // Zero fill of the dense contract.  PHASE 0 (side stream, before the walk): rows [min(2 S_k, F), F).
@@ -1068,8 +1125,7 @@ int inf3dp_extract_isocontours(const float* V, const int32_t* F, const float* fi
             INF3DP_LAUNCH_CHECK("contour_link_kernel");
             mark(5, side);
         }
-        INF3DP_CUDA(cudaFuncSetAttribute(contour_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWalkSmemBytes));
-        contour_walk_kernel<<<K, kWalkThreads, kWalkSmemBytes, side>>>(nF, w, merged, nums);
+        INF3DP_CUDA(launch_walk(nF, K, w, merged, nums, side));
         INF3DP_LAUNCH_CHECK("contour_walk_kernel");
     }
     INF3DP_CUDA(cudaEventRecord(ev_join, side));
@@ -1091,7 +1147,9 @@ int inf3dp_extract_isocontours(const float* V, const int32_t* F, const float* fi
         for (int i = 1; i < 8; ++i) cudaEventElapsedTime(&t[i], dbg_ev[0], dbg_ev[i]);
         int hdr_host[32] = {0};
         cudaMemcpy(hdr_host, w.hdr, sizeof(hdr_host), cudaMemcpyDeviceToHost);
-        fprintf(stderr, "[inf3dp contour debug] isovalues walked serially (list capacity exceeded or too large): %d of %d\n", hdr_host[8], K);
+        fprintf(stderr, "[inf3dp contour debug] isovalues walked serially (list capacity exceeded or too large): %d of %d "
+                        "(largest closed-loop count over capacity %d, open-chain count over capacity %d, piece overflow in replay %d)\n",
+                hdr_host[8], K, hdr_host[9], hdr_host[10], hdr_host[11]);
         {
             std::vector<int> cyc(K), cnt(K);
             cudaMemcpy(cyc.data(), w.cursor, K * sizeof(int), cudaMemcpyDeviceToHost);
@@ -1153,8 +1211,7 @@ int inf3dp_extract_isocontours_compact(const float* V, const int32_t* F, const f
         contour_link_kernel<<<sms * 4, 256, 0, st>>>(w);
         INF3DP_LAUNCH_CHECK("contour_link_kernel");
     }
-    INF3DP_CUDA(cudaFuncSetAttribute(contour_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWalkSmemBytes));
-    contour_walk_kernel<<<K, kWalkThreads, kWalkSmemBytes, st>>>(nF, w, rows, nums);
+    INF3DP_CUDA(launch_walk(nF, K, w, rows, nums, st));
     INF3DP_LAUNCH_CHECK("contour_walk_kernel");
     contour_export_kernel<<<(K + 255) / 256, 256, 0, st>>>(K, w, (long long*)row_offsets, row_counts);
     INF3DP_LAUNCH_CHECK("contour_export_kernel");

@@ -133,6 +133,47 @@ def test_compact_rows_equal_the_used_prefix_of_the_dense_contract(torn):
         assert len(loops[k]) == len(ref) and all(np.array_equal(a, b) for a, b in zip(loops[k], ref))
 
 
+@pytest.mark.parametrize("drop", [0.0, 0.0004])
+def test_multi_million_face_mesh_big_walk_tier(drop):
+    """F = 4 M faces (SURVEY.md 8d cfg 3, upper size): 5 - 10 k segments per isovalue, i.e. the second shared-memory tier of
+    the parallel walk (closed loops, and with faces removed open chains whose state ids need 15 bits).
+
+    At this resolution a few segments per isovalue are shorter than the reference's 1e-6 merge radius; its proximity search
+    (isocontours.cu:160-200) then strands them as extra 1-segment pieces or passes them through the other endpoint
+    (DESIGN.md divergence 1), so the comparison is the north-star one: identical segment counts, never more pieces, every
+    vertex within 1e-5 -- plus, where the piece counts agree, the SAME row order, and for our output on its own the
+    chaining invariant (consecutive rows of a piece are the two ends of one segment; closed pieces close)."""
+    from scipy.spatial import cKDTree
+    V, F = co.torus_mesh(2000, 1000)
+    f = _field(V)
+    if drop > 0:
+        rng = np.random.default_rng(17)
+        F = np.ascontiguousarray(F[rng.random(len(F)) >= drop])
+    lo, hi = float(f.min()), float(f.max())
+    iso = np.linspace(lo + 0.08 * (hi - lo), hi - 0.08 * (hi - lo), 10).astype(np.float32)
+    mo, no, so_ = co.extract_isocontours(V, F, f, iso)
+    m, n, s = _run(V, F, f, iso)
+    assert s.max() > 5120 and s.max() <= 10752, s          # the tier under test
+    assert np.array_equal(s, so_)
+    edge = 2 * np.pi * 0.9 / 1000 * 1.5                      # longest mesh edge (diagonal of a quad), generous
+    for k in range(len(iso)):
+        assert n[k] <= no[k], k
+        used, used_o = co.rows_used(m[k], n[k]), co.rows_used(mo[k], no[k])
+        assert used == s[k] + n[k] and not m[k, used:].any(), k
+        mine, theirs = co.split_rows(m[k], n[k]), co.split_rows(mo[k], no[k])
+        pm, pt = np.concatenate(mine), np.concatenate(theirs)
+        assert (cKDTree(pm).query(pt)[0] <= 1e-5).all(), k                       # every reference vertex is ours too
+        assert (cKDTree(pt).query(pm)[0] > 1e-5).sum() <= no[k], k               # ours: at most the dropped seed vertices extra
+        if n[k] == no[k]:
+            d = np.abs(m[k, :used] - mo[k, :used_o]).max(1)
+            assert d.max() <= 1e-5 and (d > 0).sum() <= 8, k                     # same order, same vertices
+        for loop in mine:
+            if len(loop) > 1:
+                assert np.linalg.norm(np.diff(loop, axis=0), axis=1).max() <= edge, k   # chained through shared segments
+            if drop == 0 and len(loop) > 50:
+                assert np.linalg.norm(loop[0] - loop[-1]) <= edge, k                   # closed mesh: loops close
+
+
 def test_full_size_properties():
     """F = 0.5 M faces, K = 200: properties that hold at any size (no O(S^2) oracle here): rows used = S_k + C_k,
     zero padding, every long loop closes, determinism."""
