@@ -80,6 +80,9 @@ int inf3dp_siren_jet(const void* packed, const float* x, int64_t n, int order, f
  * half the tensor work of the forward-mode jet.  The scratch holds the cosines of two hidden layers per resident
  * tile (256 KB per SM) between the sweeps. */
 size_t inf3dp_siren_jet_workspace_bytes(void);
+/* Process-wide cap on the SMs the persistent SIREN engines occupy (0 = all, the default).  A multi-GPU caller that overlaps
+ * the all-gather of chunk i with the query of chunk i+1 leaves a few SMs to the NCCL kernels (inf3dp/dist.py). */
+int inf3dp_siren_set_sm_limit(int max_sms);
 int inf3dp_siren_jet_ws(const void* packed, const float* x, int64_t n, int order, float* y, float* J, float* H,
                         int mode, void* workspace, size_t workspace_bytes, inf3dp_stream_t stream);
 

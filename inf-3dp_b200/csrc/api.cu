@@ -3,6 +3,8 @@
 #include <unordered_map>
 #include <string.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace inf3dp {
@@ -144,6 +146,9 @@ __global__ void unit_normals_kernel(const float* __restrict__ g, int64_t n, floa
     out[3 * i + 2] = z / nrm;
 }
 
+static std::atomic<int> g_siren_sm_limit{0};
+int siren_sm_limit() { return g_siren_sm_limit.load(); }
+
 }  // namespace inf3dp
 
 using namespace inf3dp;
@@ -152,6 +157,12 @@ extern "C" {
 
 const char* inf3dp_last_error(void) { return g_err; }
 int inf3dp_version(void) { return 100; }
+
+int inf3dp_siren_set_sm_limit(int max_sms) {
+    INF3DP_CHECK_ARG(max_sms >= 0, "siren_set_sm_limit: negative limit");
+    g_siren_sm_limit.store(max_sms);
+    return INF3DP_OK;
+}
 
 size_t inf3dp_siren_packed_bytes(int in_features, int hidden, int num_hidden_layers, int out_features) {
     if (!siren_config_supported(in_features, hidden, num_hidden_layers, out_features)) return 0;

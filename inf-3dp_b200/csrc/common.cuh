@@ -51,6 +51,14 @@ inline int num_sms() {
     return cached[dev];
 }
 
+// SMs the persistent SIREN engines may occupy (inf3dp_siren_set_sm_limit; 0 = all).  A multi-GPU caller leaves a few SMs
+// to the NCCL kernels of an all-gather that overlaps the next chunk's query.
+int siren_sm_limit();   // api.cu
+inline int siren_sms() {
+    const int all = num_sms(), lim = siren_sm_limit();
+    return (lim > 0 && lim < all) ? lim : all;
+}
+
 constexpr size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // ---------------------------------------------------------------------------------------------------------

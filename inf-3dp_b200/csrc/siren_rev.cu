@@ -759,7 +759,7 @@ int launch_rev(const void* packed, const SirenHeader& h, const float* x, int64_t
     constexpr int kTilePts = KIND == 1 ? 12 : 128;
     const int64_t tiles = (n + kTilePts - 1) / kTilePts;
     const int64_t units = (tiles + CTAS - 1) / CTAS;
-    const int64_t max_units = num_sms() / CTAS;
+    const int64_t max_units = siren_sms() / CTAS;
     const int grid = (int)(units < max_units ? units : max_units) * CTAS;
     static const bool debug = getenv("INF3DP_TC_DEBUG") != nullptr;
     unsigned long long* dbg = nullptr;

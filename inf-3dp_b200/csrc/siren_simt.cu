@@ -275,7 +275,7 @@ int launch_one(const void* packed, const SirenHeader& h, const float* x, int64_t
     INF3DP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
     constexpr int P = kRows / C;
     const int64_t tiles = (n + P - 1) / P;
-    const int grid = (int)(tiles < (int64_t)num_sms() ? tiles : (int64_t)num_sms());
+    const int grid = (int)(tiles < (int64_t)siren_sms() ? tiles : (int64_t)siren_sms());
     kern<<<grid, kThreads, kSmemBytes, stream>>>((const char*)packed, h, x, n, y, J, H);
     INF3DP_LAUNCH_CHECK("siren_simt_kernel");
     return INF3DP_OK;

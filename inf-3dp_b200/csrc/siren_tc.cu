@@ -434,7 +434,7 @@ int launch_tc(const void* packed, const SirenHeader& h, const float* x, int64_t 
     INF3DP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     constexpr int kPts = ORDER == 1 ? 32 : 128;
     const int64_t tiles = (n + kPts - 1) / kPts;
-    const int grid = (int)(tiles < (int64_t)num_sms() ? tiles : (int64_t)num_sms());
+    const int grid = (int)(tiles < (int64_t)siren_sms() ? tiles : (int64_t)siren_sms());
     static const bool debug = getenv("INF3DP_TC_DEBUG") != nullptr;
     unsigned long long* dbg = nullptr;
     if (debug) {

@@ -27,6 +27,7 @@ SIGNATURES = {
     "inf3dp_siren_pack_weights": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _sz, _vp]),
     "inf3dp_siren_jet": (_i, [_vp, _vp, _i64, _i, _vp, _vp, _vp, _i, _vp]),
     "inf3dp_siren_jet_workspace_bytes": (_sz, []),
+    "inf3dp_siren_set_sm_limit": (_i, [_i]),
     "inf3dp_siren_jet_ws": (_i, [_vp, _vp, _i64, _i, _vp, _vp, _vp, _i, _vp, _sz, _vp]),
     "inf3dp_principal_curvatures": (_i, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "inf3dp_unit_normals": (_i, [_vp, _i64, _f, _vp, _vp]),

@@ -52,3 +52,81 @@ def sharded_isocontours(vertices, faces, fields, iso_values, group=None, gather=
     if not gather or world == 1:
         return merged, nums
     return all_gather_rows(merged, K, group), all_gather_rows(nums, K, group)
+
+
+class PipelinedAllGather:
+    """All-gather of per-rank row slabs that overlaps the producer: the local rows are produced in `chunks` pieces, and
+    piece c is gathered (on a side stream for CUDA tensors) while piece c + 1 is being computed -- the one collective of
+    the sharded path costs the time of its last piece only.
+
+    Every rank holds `n_local` rows of `width` float32 columns.  The result lives in `self.gathered`
+    [chunks, world, m, width] (m = ceil(n_local / chunks); the tail of the last piece is padding);
+    `rows_of_rank(r)` is the [n_local, width] slab of rank r.
+
+        pipe = PipelinedAllGather(n_local, 4, chunks=8, device=dev)
+        for c, (lo, hi) in enumerate(pipe.ranges):
+            y, J, _ = net.query(coords[lo:hi], order=1)
+            pipe.submit(c, y, J.view(-1, 3))          # columns are concatenated into the staging rows of piece c
+        pipe.finish()                                 # the caller's stream waits for the last gather
+
+    With the persistent SIREN engines, leave a few SMs to the NCCL kernels: `reserve_sms(4)` (undo with `reserve_sms(0)`).
+    """
+
+    def __init__(self, n_local, width, chunks=8, device=None, group=None, dtype=torch.float32):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.n_local, self.width = int(n_local), int(width)
+        self.chunks = max(1, min(int(chunks), max(1, self.n_local)))
+        self.m = (self.n_local + self.chunks - 1) // self.chunks
+        self.ranges = [(min(self.n_local, c * self.m), min(self.n_local, (c + 1) * self.m)) for c in range(self.chunks)]
+        dev = torch.device(device) if device is not None else torch.device("cpu")
+        self.device = dev
+        self.staging = torch.zeros((self.chunks, self.m, self.width), dtype=dtype, device=dev)
+        self.gathered = (torch.empty((self.chunks, self.world, self.m, self.width), dtype=dtype, device=dev)
+                         if self.world > 1 else self.staging.view(self.chunks, 1, self.m, self.width))
+        self.cuda = dev.type == "cuda"
+        if self.cuda and self.world > 1:
+            self.comm = torch.cuda.Stream(dev)
+            self.events = [torch.cuda.Event() for _ in range(self.chunks)]
+
+    def submit(self, c, *columns):
+        """Pack the column blocks (each [rows, k_i], sum k_i = width) of piece c and start its all-gather."""
+        lo, hi = self.ranges[c]
+        rows = hi - lo
+        o = 0
+        for col in columns:
+            col = col.reshape(rows, -1)
+            self.staging[c, :rows, o:o + col.shape[1]] = col
+            o += col.shape[1]
+        if o != self.width:
+            raise RuntimeError(f"PipelinedAllGather.submit: got {o} columns, expected {self.width}")
+        if self.world == 1:
+            return
+        if self.cuda:
+            cur = torch.cuda.current_stream(self.device)
+            self.events[c].record(cur)
+            self.comm.wait_event(self.events[c])
+            with torch.cuda.stream(self.comm):
+                dist.all_gather_into_tensor(self.gathered[c].view(self.world * self.m, self.width), self.staging[c], group=self.group)
+        else:
+            dist.all_gather_into_tensor(self.gathered[c].view(self.world * self.m, self.width), self.staging[c], group=self.group)
+
+    def finish(self):
+        if self.cuda and self.world > 1:
+            torch.cuda.current_stream(self.device).wait_stream(self.comm)
+        return self.gathered
+
+    def rows_of_rank(self, r):
+        return self.gathered[:, r].reshape(self.chunks * self.m, self.width)[:self.n_local]
+
+
+def reserve_sms(n):
+    """Keep `n` SMs free of the persistent SIREN engines (0 = use all), so that NCCL kernels launched on another stream can
+    run next to them (include/inf3dp.h: inf3dp_siren_set_sm_limit)."""
+    from . import _lib
+    L = _lib.lib()
+    if n <= 0:
+        _lib.check(L.inf3dp_siren_set_sm_limit(0))
+        return
+    sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+    _lib.check(L.inf3dp_siren_set_sm_limit(max(2, sms - int(n))))

@@ -24,6 +24,37 @@ def _worker(rank, world, port, n):
     dist.destroy_process_group()
 
 
+def _pipe_worker(rank, world, port, n_local, chunks):
+    sys.path.insert(0, os.path.join(ROOT, "inf-3dp_b200"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from inf3dp.dist import PipelinedAllGather
+    pipe = PipelinedAllGather(n_local, 4, chunks=chunks)
+    mine = (torch.arange(n_local * 4, dtype=torch.float32).view(n_local, 4) + 1000.0 * rank)
+    for c, (lo, hi) in enumerate(pipe.ranges):
+        pipe.submit(c, mine[lo:hi, :1], mine[lo:hi, 1:])      # value column + gradient columns, as the bench does
+    pipe.finish()
+    for r in range(world):
+        want = torch.arange(n_local * 4, dtype=torch.float32).view(n_local, 4) + 1000.0 * r
+        assert torch.equal(pipe.rows_of_rank(r), want), (rank, r)
+    dist.destroy_process_group()
+
+
+def test_pipelined_all_gather_world2():
+    for n_local, chunks in ((13, 4), (16, 8), (5, 8)):
+        mp.spawn(_pipe_worker, args=(2, 29561 + n_local, n_local, chunks), nprocs=2, join=True)
+
+
+def test_pipelined_all_gather_single_process():
+    from inf3dp.dist import PipelinedAllGather
+    pipe = PipelinedAllGather(10, 4, chunks=3)
+    mine = torch.arange(40, dtype=torch.float32).view(10, 4)
+    for c, (lo, hi) in enumerate(pipe.ranges):
+        pipe.submit(c, mine[lo:hi, :1], mine[lo:hi, 1:])
+    assert torch.equal(pipe.finish().shape and pipe.rows_of_rank(0), mine)
+
+
 def test_shard_ranges_cover_exactly():
     from inf3dp.dist import shard_range
     for n in (0, 1, 7, 200, 16777216):
