@@ -291,31 +291,38 @@ isect_elect_kernel(const FieldSrc src, long long voxels, int Ns, int N1, int N2,
     }
 }
 
-__constant__ float c_off[8][3] = {  // intersection.cu:55-64
-    {-0.5f, -0.5f, -0.5f}, {0.5f, -0.5f, -0.5f}, {-0.5f, 0.5f, -0.5f}, {0.5f, 0.5f, -0.5f},
-    {-0.5f, -0.5f, 0.5f},  {0.5f, -0.5f, 0.5f},  {-0.5f, 0.5f, 0.5f},  {0.5f, 0.5f, 0.5f}};
-__constant__ int c_edge[12][2] = {  // intersection.cu:67-71
-    {0, 1}, {0, 2}, {1, 3}, {2, 3}, {4, 5}, {4, 6}, {5, 7}, {6, 7}, {0, 4}, {1, 5}, {2, 6}, {3, 7}};
+// intersection.cu:55-71: corner c sits at centre + voxel_size * (+-0.5 per axis, bit d of c = axis d), the 12 edges are
+// (0,1) (0,2) (1,3) (2,3) (4,5) (4,6) (5,7) (6,7) (0,4) (1,5) (2,6) (3,7) -- packed one nibble per edge.
+constexpr unsigned long long kEdgeC1 = 0x321065442100ull;   // first corner of edge e in bits [4e, 4e+4)
+constexpr unsigned long long kEdgeC2 = 0x765477653321ull;   // second corner
 
 // intersection.cu:135-160: sum of the edge-crossing points of one field, inclusive edge test, unguarded division.
-__device__ __forceinline__ int edge_sum(const float4 lo, const float4 hi, float iso, const float* ctr, float vs,
-                                        float* acc) {
-    const float v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-    int cnt = 0;
-    acc[0] = acc[1] = acc[2] = 0.f;
+// The 12 inclusive tests are evaluated branch-free into a mask; only the crossing edges (typically 3-6) then pay for the
+// division and the interpolation, in ascending edge order (the reference's summation order).  `sv` = this thread's
+// eight corner values in shared memory (stride kCellThreads), lo / hi = the two corner coordinates per axis.
+constexpr int kCellThreads = 256;
+__device__ __forceinline__ int edge_sum(const float4 c_lo, const float4 c_hi, const float* sv, float iso, const float* lo,
+                                        const float* hi, float* acc) {
+    const float v[8] = {c_lo.x, c_lo.y, c_lo.z, c_lo.w, c_hi.x, c_hi.y, c_hi.z, c_hi.w};
+    unsigned mask = 0;
 #pragma unroll
     for (int e = 0; e < 12; ++e) {
-        const int c1 = c_edge[e][0], c2 = c_edge[e][1];
-        const float a = v[c1], b = v[c2];
-        if (iso >= fminf(a, b) && iso <= fmaxf(a, b)) {
-            const float t = __fdiv_rn(iso - a, b - a);
+        const float a = v[(kEdgeC1 >> (4 * e)) & 15], b = v[(kEdgeC2 >> (4 * e)) & 15];
+        mask |= (iso >= fminf(a, b) && iso <= fmaxf(a, b)) ? (1u << e) : 0u;
+    }
+    const int cnt = __popc(mask);
+    acc[0] = acc[1] = acc[2] = 0.f;
+    while (mask) {
+        const int e = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const int c1 = (int)((kEdgeC1 >> (4 * e)) & 15), c2 = (int)((kEdgeC2 >> (4 * e)) & 15);
+        const float a = sv[c1 * kCellThreads], b = sv[c2 * kCellThreads];
+        const float t = __fdiv_rn(iso - a, b - a);
 #pragma unroll
-            for (int d = 0; d < 3; ++d) {
-                const float x1 = fmaf(vs, c_off[c1][d], ctr[d]);
-                const float x2 = fmaf(vs, c_off[c2][d], ctr[d]);
-                acc[d] += fmaf(t, x2 - x1, x1);
-            }
-            ++cnt;
+        for (int d = 0; d < 3; ++d) {
+            const float x1 = ((c1 >> d) & 1) ? hi[d] : lo[d];
+            const float x2 = ((c2 >> d) & 1) ? hi[d] : lo[d];
+            acc[d] += fmaf(t, x2 - x1, x1);
         }
     }
     return cnt;
@@ -334,6 +341,7 @@ __global__ void __launch_bounds__(256)
 isect_cell_kernel(const FieldSrc src, const float* __restrict__ s_iso, const float* __restrict__ a_iso,
                   const float* __restrict__ b_iso, int Dx, int Ns, int N1, int N2, long long tiles, IsectWs w,
                   uint8_t* __restrict__ mask, int16_t* __restrict__ idx, float* __restrict__ pts) {
+    __shared__ float s_corner[3 * 8 * kCellThreads];   // [field][corner][thread]
     const float vs = (float)(2.0 / (double)(float)Dx);  // intersection.cu:54
     const int tiles2 = (N2 + kCellTile2 - 1) / kCellTile2;
     const int r = threadIdx.x >> 5, q = threadIdx.x & 31;
@@ -356,10 +364,21 @@ isect_cell_kernel(const FieldSrc src, const float* __restrict__ s_iso, const flo
         load_voxel<GRID, false>(src, v, f);
         float ctr[3];
         load_center<GRID>(src, v, ctr);
+        // corner coordinates: centre + voxel_size * (-0.5 | +0.5), the two values per axis shared by all three fields
+        float lo[3], hi[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) { lo[d] = fmaf(vs, -0.5f, ctr[d]); hi[d] = fmaf(vs, 0.5f, ctr[d]); }
+        float* sv = s_corner + threadIdx.x;
+        auto stage = [&](int fi, const float4 a, const float4 b) {
+            float* q = sv + fi * 8 * kCellThreads;
+            q[0] = a.x; q[kCellThreads] = a.y; q[2 * kCellThreads] = a.z; q[3 * kCellThreads] = a.w;
+            q[4 * kCellThreads] = b.x; q[5 * kCellThreads] = b.y; q[6 * kCellThreads] = b.z; q[7 * kCellThreads] = b.w;
+        };
+        stage(0, f.a[0], f.a[1]); stage(1, f.b[0], f.b[1]); stage(2, f.s[0], f.s[1]);   // read back by this thread only
         float pa[3], pb[3], ps[3];
-        const int ca = edge_sum(f.a[0], f.a[1], a_iso[i1], ctr, vs, pa);
-        const int cb = edge_sum(f.b[0], f.b[1], b_iso[i2], ctr, vs, pb);
-        const int cs = edge_sum(f.s[0], f.s[1], s_iso[is], ctr, vs, ps);
+        const int ca = edge_sum(f.a[0], f.a[1], sv, a_iso[i1], lo, hi, pa);
+        const int cb = edge_sum(f.b[0], f.b[1], sv + 8 * kCellThreads, b_iso[i2], lo, hi, pb);
+        const int cs = edge_sum(f.s[0], f.s[1], sv + 16 * kCellThreads, s_iso[is], lo, hi, ps);
         idx[3 * c] = (int16_t)is; idx[3 * c + 1] = (int16_t)i1; idx[3 * c + 2] = (int16_t)i2;
         mask[c] = 1;
 #pragma unroll
