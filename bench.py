@@ -446,7 +446,12 @@ def run_ours(args):
     e2e_checksum = float(out_host[:: max(1, n // 4096), 0].double().sum())
 
     # max over ranks
+    rank_ms = None
     if world > 1:
+        mine_ms = torch.tensor([ms_step], dtype=torch.float64, device=dev)
+        all_ms = torch.empty(world, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(all_ms, mine_ms)
+        rank_ms = [round(float(v), 3) for v in all_ms.tolist()]
         tt = torch.tensor([ms_step, ms_kernel, ms_e2e], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms_step, ms_kernel, ms_e2e = [float(v) for v in tt.tolist()]
@@ -469,7 +474,8 @@ def run_ours(args):
                         "sample": "262144 grid points, best of 2, oracle/siren_torch_port.field_query_with_grads (torch CPU)"}
         line = {
             "metric": "siren_value_grad_points_per_s", "value": value, "unit": "points/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "ms_per_step_by_rank": rank_ms,
+            "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": dtype_note,
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "network": "3-256-256-256-256-1 sine, random init seed 2048",
