@@ -134,3 +134,30 @@ def test_marching_cubes_nan_mask_and_empty():
     assert len(v0) == 0 and len(f0) == 0
     v1, f1, _, _ = vo.marching_cubes(sdf[:1], 0.0)                 # a slab one sample thick has no cubes
     assert len(v1) == 0 and len(f1) == 0
+
+
+def test_volume_api_has_no_cpu_fallback():
+    """The product entry points reject host tensors (as CHECK_CUDA does in the reference, contour_cuda/includes/utils.h:6-8)
+    and never route through the oracle."""
+    import torch
+    import inf3dp
+    vol = torch.zeros((4, 4, 4))
+    with pytest.raises(RuntimeError):
+        inf3dp.marching_cubes(vol, 0.0)
+    with pytest.raises(RuntimeError):
+        inf3dp.get_fields_intersection_from_grids(vol, vol, vol, torch.zeros(2), torch.zeros(2), torch.zeros(2))
+    with pytest.raises(RuntimeError):
+        inf3dp.grid_queries(8, device="cpu")
+    src = open(os.path.join(ROOT, "inf-3dp_b200", "inf3dp", "volume.py")).read()
+    assert "oracle" not in src.replace("no CPU fallback", "")
+
+
+def test_c_abi_rejects_bad_volume_arguments():
+    from inf3dp import _lib
+    L = _lib.lib()
+    assert L.inf3dp_marching_cubes_workspace_bytes(0, 4, 4) == 0
+    assert L.inf3dp_marching_cubes_workspace_bytes(64, 64, 64) >= 64 ** 3 * 6
+    assert L.inf3dp_grid_queries(1, 1.0, 0, 0, None, None) == _lib.EINVAL              # N < 2
+    assert L.inf3dp_grid_queries(8, 1.0, 500, 100, None, None) == _lib.EINVAL          # range outside the grid
+    assert L.inf3dp_marching_cubes_count(None, 4, 4, 4, 0.0, None, 0, None, None) == _lib.EINVAL
+    assert L.inf3dp_siren_set_sm_limit(-1) == _lib.EINVAL and L.inf3dp_siren_set_sm_limit(0) == _lib.OK
