@@ -377,11 +377,15 @@ def run_ours(args):
             inf3dp.unit_normals(J.view(n, 3), out=normals)           # launch 2: normals
             return y, J
         for c, (lo, hi) in enumerate(pipe.ranges):
-            y, J, _ = net.query(coords[lo:hi], order=1, mode=engine)
-            inf3dp.unit_normals(J.view(hi - lo, 3), out=normals[lo:hi])
-            pipe.submit(c, y, J.view(hi - lo, 3))
+            if engine == "tc_reverse":   # (value, grad) rows written straight into the all-gather's staging buffer
+                rows = net.query_rows(coords[lo:hi], out=pipe.slot(c))
+                inf3dp.unit_normals_rows(rows, out=normals[lo:hi])
+                pipe.gather(c)
+            else:
+                y, J, _ = net.query(coords[lo:hi], order=1, mode=engine)
+                inf3dp.unit_normals(J.view(hi - lo, 3), out=normals[lo:hi])
+                pipe.submit(c, y, J.view(hi - lo, 3))
         pipe.finish()
-        return y, J
 
     # kernel-only timing of the dominant kernel (for the roofline), same stream
     def jet_only():

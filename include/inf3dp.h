@@ -90,6 +90,14 @@ int inf3dp_siren_jet_ws(const void* packed, const float* x, int64_t n, int order
  * field_query_with_grads, toolpath_utils.py:180-181).  In-place (normals == grad) is allowed. */
 int inf3dp_unit_normals(const float* grad, int64_t n, float eps, float* normals, inf3dp_stream_t stream);
 
+/* Value + gradient of a single-output field network (the reverse-mode engine of inf3dp_siren_jet_ws, order 1) written as
+ * packed rows [n,4] = (value, d/dx, d/dy, d/dz), 16-byte aligned: the layout of the reference's host result
+ * (utils.py:249-253 concatenates fields and grads) and of the multi-GPU all-gather, one 16-byte store per point.
+ * inf3dp_unit_normals_rows is inf3dp_unit_normals on such rows. */
+int inf3dp_siren_value_grad_rows(const void* packed, const float* x, int64_t n, float* rows, void* workspace,
+                                 size_t workspace_bytes, inf3dp_stream_t stream);
+int inf3dp_unit_normals_rows(const float* rows, int64_t n, float eps, float* normals, inf3dp_stream_t stream);
+
 /* Curvature tail.  Replaces the per-point Python loop of diff_operators.py:167-220 (min_max_curvs_and_vectors)
  * and construct_tangent_basis (:280-298): grad [n,3], hess [n,3,3] -> kappa [n,2] (min,max), dirs [n,2,3]. */
 int inf3dp_principal_curvatures(const float* grad, const float* hess, int64_t n, float* kappa, float* dirs,

@@ -136,6 +136,18 @@ __global__ void principal_curvatures_kernel(const float* __restrict__ grad, cons
 
 // Unit normals from gradients: out = g / max(|g|, eps)  (torch.nn.functional.normalize semantics, the step the
 // reference applies after field_query_with_grads, e.g. toolpath_utils.py:180-181).  One thread per point.
+// the same on packed (value, d/dx, d/dy, d/dz) rows: identical arithmetic, gradient read as one 16-byte load
+__global__ void unit_normals_rows_kernel(const float* __restrict__ rows, int64_t n, float eps, float* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 r = __ldg(reinterpret_cast<const float4*>(rows) + i);
+    const float x = r.y, y = r.z, z = r.w;
+    const float nrm = fmaxf(sqrtf(x * x + y * y + z * z), eps);
+    out[3 * i] = x / nrm;
+    out[3 * i + 1] = y / nrm;
+    out[3 * i + 2] = z / nrm;
+}
+
 __global__ void unit_normals_kernel(const float* __restrict__ g, int64_t n, float eps, float* __restrict__ out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -283,6 +295,29 @@ int inf3dp_siren_jet_ws(const void* packed, const float* x, int64_t n, int order
 int inf3dp_siren_jet(const void* packed, const float* x, int64_t n, int order, float* y, float* J, float* H,
                      int mode, inf3dp_stream_t stream) {
     return inf3dp_siren_jet_ws(packed, x, n, order, y, J, H, mode, nullptr, 0, stream);
+}
+
+int inf3dp_siren_value_grad_rows(const void* packed, const float* x, int64_t n, float* rows, void* workspace,
+                                 size_t workspace_bytes, inf3dp_stream_t stream) {
+    INF3DP_CHECK_ARG(packed != nullptr, "siren_value_grad_rows: null packed weights");
+    INF3DP_CHECK_ARG(n >= 0, "siren_value_grad_rows: negative point count");
+    if (n == 0) return INF3DP_OK;
+    INF3DP_CHECK_ARG(x && rows, "siren_value_grad_rows: null x or rows");
+    SirenHeader h;
+    int rc = lookup_header(packed, &h);
+    if (rc != INF3DP_OK) return rc;
+    INF3DP_CHECK_ARG(h.rev_ok, "siren_value_grad_rows: needs a single-output sine network 3-256-256-256-256-1");
+    return siren_rev_launch_rows(packed, h, x, n, rows, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int inf3dp_unit_normals_rows(const float* rows, int64_t n, float eps, float* normals, inf3dp_stream_t stream) {
+    INF3DP_CHECK_ARG(n >= 0, "unit_normals_rows: negative n");
+    if (n == 0) return INF3DP_OK;
+    INF3DP_CHECK_ARG(rows && normals, "unit_normals_rows: null pointer");
+    INF3DP_CHECK_ARG((reinterpret_cast<uintptr_t>(rows) & 15) == 0, "unit_normals_rows: rows must be 16-byte aligned");
+    unit_normals_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rows, n, eps, normals);
+    INF3DP_LAUNCH_CHECK("unit_normals_rows_kernel");
+    return INF3DP_OK;
 }
 
 int inf3dp_unit_normals(const float* grad, int64_t n, float eps, float* normals, inf3dp_stream_t stream) {

@@ -143,6 +143,8 @@ int siren_rev_pack(const float* const* W, float omega0, const uint32_t* maxabs_b
                    SirenHeader& hdr, cudaStream_t stream);
 int siren_rev_launch(const void* packed, const SirenHeader& h, const float* x, int64_t n, float* y, float* J, void* ws,
                      size_t ws_bytes, cudaStream_t stream);
+int siren_rev_launch_rows(const void* packed, const SirenHeader& h, const float* x, int64_t n, float* rows, void* ws,
+                          size_t ws_bytes, cudaStream_t stream);
 int siren_mlp_pack(const float* const* W, const float* const* b, int out_features, void* packed, const SirenLayout& lay,
                    SirenHeader& hdr, cudaStream_t stream);
 int siren_mlp_launch(const void* packed, const SirenHeader& h, const float* x, int64_t n, float* y, cudaStream_t stream);

@@ -644,10 +644,14 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
                     r4[o] = ((s_part[(0 * 4 + o) * 128 + row] + s_part[(1 * 4 + o) * 128 + row]) +
                              s_part[(2 * 4 + o) * 128 + row]) + s_part[(3 * 4 + o) * 128 + row];
                 const float inv_g = s_misc[4];
-                y[pt] = r4[0] + s_misc[3];
-                J[3 * pt] = r4[1] * inv_g;
-                J[3 * pt + 1] = r4[2] * inv_g;
-                J[3 * pt + 2] = r4[3] * inv_g;
+                if (Hout != nullptr) {   // packed rows (value, d/dx, d/dy, d/dz): one 16-byte store per point
+                    reinterpret_cast<float4*>(Hout)[pt] = make_float4(r4[0] + s_misc[3], r4[1] * inv_g, r4[2] * inv_g, r4[3] * inv_g);
+                } else {
+                    y[pt] = r4[0] + s_misc[3];
+                    J[3 * pt] = r4[1] * inv_g;
+                    J[3 * pt + 1] = r4[2] * inv_g;
+                    J[3 * pt + 2] = r4[3] * inv_g;
+                }
             }
             // Hazards into the next unit: the next tile's layer 0 overwrote exactly the accumulator slices this warp had
             // finished reading (tcgen05.wait::ld before the math of each round); s_part is rewritten only after six more
@@ -856,6 +860,17 @@ int siren_rev_launch(const void* packed, const SirenHeader& h, const float* x, i
     static const int ctas = [] { const char* e = getenv("INF3DP_REV_CTAS"); return e && atoi(e) == 1 ? 1 : 2; }();
     return ctas == 1 ? launch_rev<1, 0>(packed, h, x, n, y, J, nullptr, ws, stream)
                      : launch_rev<2, 0>(packed, h, x, n, y, J, nullptr, ws, stream);
+}
+
+// Same query with the outputs packed as rows (value, d/dx, d/dy, d/dz) of a [n,4] tensor.
+int siren_rev_launch_rows(const void* packed, const SirenHeader& h, const float* x, int64_t n, float* rows, void* ws,
+                          size_t ws_bytes, cudaStream_t stream) {
+    INF3DP_CHECK_ARG(h.rev_ok && h.off_rev != 0, "siren_rev: packed weights carry no reverse-mode section");
+    INF3DP_CHECK_ARG(ws != nullptr && ws_bytes >= siren_rev_workspace_bytes(),
+                     "siren_rev: workspace of %zu bytes needed (inf3dp_siren_jet_workspace_bytes), got %zu",
+                     siren_rev_workspace_bytes(), ws_bytes);
+    INF3DP_CHECK_ARG((reinterpret_cast<uintptr_t>(rows) & 15) == 0, "siren_rev: rows must be 16-byte aligned");
+    return launch_rev<2, 0>(packed, h, x, n, nullptr, nullptr, rows, ws, stream);
 }
 
 // Value + gradient + Hessian (order 2) of single-output networks: forward-mode second-order jet on the CTA-pair engine.

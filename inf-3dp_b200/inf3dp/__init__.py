@@ -8,7 +8,7 @@ from .siren import SingleBVPNet, MLPClassifier, set_engine, get_engine
 from .contours import (extract_isocontours, get_fields_intersection_inter_slice, extract_isocontours_raw,
                        extract_isocontours_compact, contour_loops)
 from .diffops import (gradient, hessian, hessian3d, jacobian, divergence, laplace, principal_curvatures,
-                      min_max_curvs_and_vectors, unit_normals)
+                      min_max_curvs_and_vectors, unit_normals, unit_normals_rows)
 from .query import field_querying, field_query_with_grads, HostPipeline
 from .projection import batch_isosurface_projection, iter_project_contours_batch
 from .volume import (grid_queries, grid_field, get_grid_fields, marching_cubes, sdf_to_mesh, gen_iso_layers,
@@ -32,7 +32,7 @@ __all__ = [
     "SingleBVPNet", "MLPClassifier", "set_engine", "get_engine", "extract_isocontours",
     "get_fields_intersection_inter_slice", "extract_isocontours_raw", "extract_isocontours_compact", "contour_loops",
     "gradient", "hessian", "hessian3d", "jacobian",
-    "divergence", "laplace", "principal_curvatures", "min_max_curvs_and_vectors", "unit_normals", "field_querying",
+    "divergence", "laplace", "principal_curvatures", "min_max_curvs_and_vectors", "unit_normals", "unit_normals_rows", "field_querying",
     "field_query_with_grads", "HostPipeline", "patch_reference", "batch_isosurface_projection",
     "iter_project_contours_batch", "CollTVSDF", "collision_evaluation", "tvsdf_collision_forward", "quat_collision_sweep",
     "transform_nozzle_pcd_with_quaternion", "grid_queries", "grid_field", "get_grid_fields", "marching_cubes",

@@ -124,6 +124,17 @@ def unit_normals(grads, eps=1e-12, out=None):
     return out
 
 
+def unit_normals_rows(rows, eps=1e-12, out=None):
+    """unit_normals on packed (value, d/dx, d/dy, d/dz) rows [n,4] -> [n,3]."""
+    if not rows.is_cuda or rows.dtype != torch.float32 or not rows.is_contiguous() or rows.shape[-1] != 4:
+        raise RuntimeError("inf3dp: unit_normals_rows needs a contiguous CUDA float32 [n,4] tensor (no CPU fallback)")
+    n = rows.numel() // 4
+    out = torch.empty((n, 3), dtype=torch.float32, device=rows.device) if out is None else out
+    with torch.cuda.device(rows.device):
+        _lib.check(_lib.lib().inf3dp_unit_normals_rows(_lib.ptr(rows), n, float(eps), _lib.ptr(out), _lib.stream_ptr(rows.device)))
+    return out
+
+
 def min_max_curvs_and_vectors(f, x_temp):
     """diff_operators.py:167-220: f maps [N,3] coords to the {'model_in','model_out'} dict of a fused network."""
     x_temp = x_temp.clone().detach().requires_grad_(True)

@@ -89,6 +89,24 @@ class PipelinedAllGather:
             self.comm = torch.cuda.Stream(dev)
             self.events = [torch.cuda.Event() for _ in range(self.chunks)]
 
+    def slot(self, c):
+        """Staging rows of piece c ([hi - lo, width] view): a producer may write them in place and then call gather(c)."""
+        lo, hi = self.ranges[c]
+        return self.staging[c, :hi - lo]
+
+    def gather(self, c):
+        """Start the all-gather of piece c (its staging rows were written on the current stream)."""
+        if self.world == 1:
+            return
+        if self.cuda:
+            cur = torch.cuda.current_stream(self.device)
+            self.events[c].record(cur)
+            self.comm.wait_event(self.events[c])
+            with torch.cuda.stream(self.comm):
+                dist.all_gather_into_tensor(self.gathered[c].view(self.world * self.m, self.width), self.staging[c], group=self.group)
+        else:
+            dist.all_gather_into_tensor(self.gathered[c].view(self.world * self.m, self.width), self.staging[c], group=self.group)
+
     def submit(self, c, *columns):
         """Pack the column blocks (each [rows, k_i], sum k_i = width) of piece c and start its all-gather."""
         lo, hi = self.ranges[c]
@@ -100,16 +118,7 @@ class PipelinedAllGather:
             o += col.shape[1]
         if o != self.width:
             raise RuntimeError(f"PipelinedAllGather.submit: got {o} columns, expected {self.width}")
-        if self.world == 1:
-            return
-        if self.cuda:
-            cur = torch.cuda.current_stream(self.device)
-            self.events[c].record(cur)
-            self.comm.wait_event(self.events[c])
-            with torch.cuda.stream(self.comm):
-                dist.all_gather_into_tensor(self.gathered[c].view(self.world * self.m, self.width), self.staging[c], group=self.group)
-        else:
-            dist.all_gather_into_tensor(self.gathered[c].view(self.world * self.m, self.width), self.staging[c], group=self.group)
+        self.gather(c)
 
     def finish(self):
         if self.cuda and self.world > 1:

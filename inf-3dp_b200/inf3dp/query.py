@@ -77,6 +77,10 @@ class HostPipeline:
         self.net = _net_of(decoder)
         self.chunk = int(chunk)
         self.mode = mode
+        self.rows_engine = mode in (None, "auto", "tc_reverse") and hasattr(self.net, "query_rows") and \
+            getattr(self.net, "out_features", 0) == 1 and getattr(self.net, "in_features", 0) == 3 and \
+            getattr(self.net, "type", "") == "sine" and getattr(self.net, "hidden_features", 0) == 256 and \
+            getattr(self.net, "num_hidden_layers", 0) == 3
         self.device = torch.device(device if device is not None else torch.cuda.current_device())
         if self.device.type != "cuda":
             raise RuntimeError("inf3dp.HostPipeline needs a CUDA device")
@@ -107,9 +111,12 @@ class HostPipeline:
             cur.wait_event(self.ev_in[b])
             if i >= 2:
                 cur.wait_event(self.ev_out[b])  # the D2H that read this output buffer is done
-            y, J, _ = self.net.query(self.d_x[b][:m], order=1, mode=self.mode)
-            self.d_o[b][:m, 0:1].copy_(y)
-            self.d_o[b][:m, 1:4].copy_(J[:, 0, :])
+            if self.rows_engine:   # the reverse-mode engine writes the (value, grad) rows in place
+                self.net.query_rows(self.d_x[b][:m], out=self.d_o[b][:m])
+            else:
+                y, J, _ = self.net.query(self.d_x[b][:m], order=1, mode=self.mode)
+                self.d_o[b][:m, 0:1].copy_(y)
+                self.d_o[b][:m, 1:4].copy_(J[:, 0, :])
             self.ev_k[b].record(cur)
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(self.ev_k[b])

@@ -111,6 +111,24 @@ def jet(blob, x, order, out_features, mode=None):
     return y, J, H
 
 
+def value_grad_rows(blob, x, out=None):
+    """x [n,3] (CUDA, f32) -> rows [n,4] = (value, d/dx, d/dy, d/dz) from the reverse-mode engine, optionally into `out`."""
+    if not x.is_cuda:
+        raise RuntimeError("inf3dp: coords must be a CUDA tensor (no CPU fallback)")
+    x = x.detach().to(torch.float32).contiguous()
+    n = x.shape[0]
+    dev = x.device
+    if out is None:
+        out = torch.empty((n, 4), dtype=torch.float32, device=dev)
+    elif (not out.is_cuda or out.dtype != torch.float32 or not out.is_contiguous() or out.numel() < 4 * n):
+        raise RuntimeError("inf3dp: `out` must be a contiguous CUDA float32 tensor with room for [n,4] rows")
+    ws = _jet_workspace(dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().inf3dp_siren_value_grad_rows(_lib.ptr(blob), _lib.ptr(x), n, _lib.ptr(out), _lib.ptr(ws),
+                                                           ws.numel(), _lib.stream_ptr(dev)))
+    return out.view(-1, 4)[:n] if out.dim() != 2 or out.shape[0] != n else out
+
+
 class _SirenJacobian(torch.autograd.Function):
     """J(x) as a differentiable node: its backward contracts with the Hessian of an order-2 launch."""
 
@@ -185,6 +203,15 @@ class FusedSirenMixin:
         if H is not None:
             H = H.view(*lead, self.out_features, 3, 3)
         return y, J, H
+
+
+    @torch.no_grad()
+    def query_rows(self, coords, out=None):
+        """Value + gradient as packed rows [n,4] = (value, d/dx, d/dy, d/dz) (single-output sine field networks): the
+        layout of the reference's host result (utils.py:249-253) and of the multi-GPU all-gather."""
+        ws, bs = self._weights()
+        blob = self._packed.get(ws, bs)
+        return value_grad_rows(blob, coords.reshape(-1, coords.shape[-1]), out)
 
 
 class SingleBVPNet(FusedSirenMixin, nn.Module):

@@ -38,6 +38,14 @@ def _pipe_worker(rank, world, port, n_local, chunks):
     for r in range(world):
         want = torch.arange(n_local * 4, dtype=torch.float32).view(n_local, 4) + 1000.0 * r
         assert torch.equal(pipe.rows_of_rank(r), want), (rank, r)
+    # in-place producer: write the staging rows of a piece directly, then gather it
+    for c, (lo, hi) in enumerate(pipe.ranges):
+        pipe.slot(c).copy_(-mine[lo:hi])
+        pipe.gather(c)
+    pipe.finish()
+    for r in range(world):
+        want = -(torch.arange(n_local * 4, dtype=torch.float32).view(n_local, 4) + 1000.0 * r)
+        assert torch.equal(pipe.rows_of_rank(r), want), (rank, r)
     dist.destroy_process_group()
 
 

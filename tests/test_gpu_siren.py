@@ -297,3 +297,29 @@ def test_reverse_engine_range_scale_with_large_weights(golden, gain):
         err[eng] = (np.abs(y.cpu().numpy() - yo).max(), so.angle_deg(J.cpu().numpy()[:, 0], Jo[:, 0]).max())
     assert err["tc_reverse"][0] <= max(TOL_F, 4 * err["simt"][0])
     assert err["tc_reverse"][1] <= max(TOL_ANGLE, 4 * err["simt"][1])
+
+
+@pytest.mark.gpu
+def test_packed_rows_equal_value_and_gradient(golden):
+    """inf3dp_siren_value_grad_rows / inf3dp_unit_normals_rows: the packed (value, grad) rows are bit-identical to the
+    separate y / J outputs of the same engine, also for ragged sizes and when written into a caller's buffer."""
+    import inf3dp
+    net = inf3dp.SingleBVPNet(type="sine", in_features=3)
+    net.load_state_dict({k[4:]: torch.from_numpy(np.asarray(golden[k])) for k in golden.files if k.startswith("sdf/net.")})
+    net = net.cuda()
+    g = torch.Generator(device="cpu").manual_seed(3)
+    for n in (1, 127, 1024, 100_003):
+        x = (torch.rand((n, 3), generator=g) * 2 - 1).cuda()
+        y, J, _ = net.query(x, order=1, mode="tc_reverse")
+        rows = net.query_rows(x)
+        assert rows.shape == (n, 4)
+        assert torch.equal(rows[:, :1], y) and torch.equal(rows[:, 1:], J[:, 0, :])
+        buf = torch.full((n + 5, 4), -7.0, device="cuda")
+        out = net.query_rows(x, out=buf[:n])
+        assert out.data_ptr() == buf.data_ptr() and torch.equal(out, rows) and bool((buf[n:] == -7.0).all())
+        assert torch.equal(inf3dp.unit_normals_rows(rows), inf3dp.unit_normals(J[:, 0, :].contiguous()))
+    with pytest.raises(RuntimeError):
+        net.query_rows(x.cpu())
+    quat = inf3dp.SingleBVPNet(type="sine", in_features=3, out_features=4).cuda()
+    with pytest.raises(RuntimeError):
+        quat.query_rows(x)          # rows are the single-output field layout
