@@ -161,3 +161,34 @@ def test_c_abi_rejects_bad_volume_arguments():
     assert L.inf3dp_grid_queries(8, 1.0, 500, 100, None, None) == _lib.EINVAL          # range outside the grid
     assert L.inf3dp_marching_cubes_count(None, 4, 4, 4, 0.0, None, 0, None, None) == _lib.EINVAL
     assert L.inf3dp_siren_set_sm_limit(-1) == _lib.EINVAL and L.inf3dp_siren_set_sm_limit(0) == _lib.OK
+
+
+def test_marching_cubes_random_volumes_property():
+    """Random small volumes (smooth + noise, random shapes, levels, NaN holes): one vertex per sign-changing edge between
+    finite samples that touches a valid cube, every referenced vertex exists, every mesh edge away from holes and the grid
+    border is shared by an even number of triangles, and 'ascent' is 'descent' with every triangle flipped."""
+    rng = np.random.default_rng(42)
+    for trial in range(40):
+        shape = tuple(int(v) for v in rng.integers(2, 9, 3))
+        vol = rng.standard_normal(shape).astype(np.float32)
+        if trial % 3 == 0:
+            vol[rng.random(shape) < 0.1] = np.nan
+        level = float(rng.uniform(-0.5, 0.5))
+        v, f, n, val = vo.marching_cubes(vol, level, (1.0, 1.0, 1.0), "descent")
+        va, fa, na, vala = vo.marching_cubes(vol, level, (1.0, 1.0, 1.0), "ascent")
+        assert np.array_equal(v, va) and np.array_equal(val, vala) and np.array_equal(n, -na)
+        assert np.array_equal(f, fa[:, [0, 2, 1]])
+        if len(f):
+            assert f.min() >= 0 and f.max() < len(v) and len(np.unique(f)) == len(v)
+        assert np.isfinite(v).all() and np.isfinite(n).all()
+        assert len(v) <= _crossing_edges(vol, level)
+        if not np.isnan(vol).any():
+            # closed except on the grid border: pad with a far-outside shell and the surface must close completely
+            pad = np.full(tuple(s + 2 for s in shape), 100.0, np.float32)
+            pad[1:-1, 1:-1, 1:-1] = vol
+            vp, fp, _, _ = vo.marching_cubes(pad, level)
+            assert len(vp) == _crossing_edges(pad, level)
+            d = np.concatenate([fp[:, [0, 1]], fp[:, [1, 2]], fp[:, [2, 0]]], 0).astype(np.int64)
+            u = np.sort(d, 1)
+            _, cnt = np.unique(u[:, 0] * max(len(vp), 1) + u[:, 1], return_counts=True)
+            assert (cnt % 2 == 0).all()
