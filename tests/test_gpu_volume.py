@@ -214,13 +214,15 @@ def test_intersection_on_grids_equals_the_expanded_path(N, Ns, N1, N2):
 
 
 def test_marching_cubes_random_volumes_bit_exact():
-    """Random shapes (both count kernels: Gz % 4 == 0 takes the vectorised one), levels, NaN / inf holes, both orientations:
-    every array bit-identical to the oracle."""
+    """Random shapes (all three count paths: Gz % 32 == 0 bit volume, Gz % 4 == 0 vectorised, scalar), levels, NaN / inf
+    holes, both orientations: every array bit-identical to the oracle."""
     rng = np.random.default_rng(7)
     for trial in range(40):
         shape = [int(v) for v in rng.integers(2, 40, 3)]
         if trial % 2 == 0:
             shape[2] = 4 * max(1, shape[2] // 4)
+        if trial % 4 == 1:
+            shape[2] = 32 * int(rng.integers(1, 4))          # the bit-volume count path (Gz % 32 == 0)
         vol = rng.standard_normal(shape).astype(np.float32)
         if trial % 3 == 0:
             vol[rng.random(shape) < 0.05] = np.nan
