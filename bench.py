@@ -149,7 +149,7 @@ def run_reference(args):
     emit_json_line(line)
 
 
-def bench_isocontours(dev, peaks):
+def bench_isocontours(dev, peaks, cpu_baseline=False):
     """BASELINE.json configs[2]: 200-isovalue isocontour extraction on a closed synthetic mesh (SURVEY.md 8d cfg 3)."""
     import numpy as np
     import torch
@@ -188,7 +188,30 @@ def bench_isocontours(dev, peaks):
     S = int(sum(seg)); C = int(nums.sum().item())
     contract = 12 * nF + 16 * nV + 4 * K + 12 * K * nF + 4 * K
     useful = 12 * nF + 16 * nV + 4 * K + 12 * (S + C) + 4 * K
+    cpu = None
+    if cpu_baseline:
+        # reported baseline (rank 0, N = 1): the single-thread C restatement of the reference kernels on a bounded sample of
+        # the same workload (the reference has no CPU implementation of this op); checked against the GPU rows while at it
+        sel = np.ascontiguousarray(iso[::25][:8])
+        t0 = time.perf_counter()
+        mo, no, so_ = co.extract_isocontours(V, F, f, sel)
+        dt = time.perf_counter() - t0
+        rows = differ = 0
+        worst = 0.0
+        for j, k in enumerate(range(0, K, 25)[:8]):     # same piece count => same row order: compare row by row
+            if int(nums[k]) == int(no[j]):
+                mine = merged[k].cpu().numpy()
+                used = int(so_[j]) + int(no[j])
+                d = np.abs(mine[:used] - mo[j][:used]).max(axis=1) if used else np.zeros(0)
+                rows += used
+                differ += int((d > 0).sum())
+                worst = max(worst, float(d.max()) if used else 0.0)
+        cpu = {"value": len(sel) / dt, "unit": "layers/s", "cores": 1, "kind": "port",
+               "sample": f"{len(sel)} of the {K} isovalues, oracle/contour_oracle.c (gcc -O2, one thread)",
+               # segments shorter than the reference's 1e-6 merge radius can be entered through either end (DESIGN.md divergence 1)
+               "check_vs_gpu": {"rows_compared": rows, "rows_not_bit_identical": differ, "max_abs_vertex_diff": worst}}
     return {"metric": "isocontour_layers_per_s", "value": K / (ms / 1e3), "unit": "layers/s", "ms_per_call": ms,
+            "cpu_baseline": cpu,
             "config": {"workload": "200-isovalue isocontour extraction, closed torus mesh", "faces": nF,
                        "vertices": nV, "isovalues": K, "segments": S, "loops": C},
             "roofline": {"bound": "hbm", "achieved": contract / (ms / 1e3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
@@ -463,7 +486,7 @@ def run_ours(args):
     # The other configurations of BASELINE.json (isovalues, Hessian sweep, collision waypoints) shard without any exchange:
     # at N > 1 every rank runs its own copy of the workload (weak scaling, rank-local consumers), the time is the maximum
     # over ranks and the reported value is the aggregate of all ranks.
-    iso = bench_isocontours(dev, peaks)
+    iso = bench_isocontours(dev, peaks, cpu_baseline=(world == 1 and rank == 0))
     hess = bench_hessian_sweep(net, dev, peaks)
     coll = bench_collision(net, dev)
     if world > 1:
