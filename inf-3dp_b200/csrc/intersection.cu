@@ -100,15 +100,52 @@ __device__ __forceinline__ bool min_max8(const float4 lo, const float4 hi, float
     return true;
 }
 
+// First sorted position p with !PRED(sorted[p]) where PRED is monotone (true ... true false ... false): a lower / upper
+// bound.  Isovalue sets are almost always evenly spaced (np.linspace, toolpath_utils.py:223), so the search starts at the
+// position linear interpolation predicts and gallops from there: 2-3 probes instead of log2(n) for such sets, never more
+// than ~2 log2(n) for arbitrary ones; the result is exactly the binary search's.
+template <typename Pred>
+__device__ __forceinline__ int bound_from_guess(const float* __restrict__ sorted, int n, int guess, Pred pred) {
+    if (n <= 0) return 0;
+    int g = min(max(guess, 0), n - 1);
+    int lo, hi;                                   // invariant: pred holds on [.., lo), fails on [hi, ..)
+    if (pred(sorted[g])) {
+        lo = g + 1;
+        int step = 1;
+        hi = n;
+        while (lo < n) {
+            const int probe = min(lo + step - 1, n - 1);
+            if (!pred(sorted[probe])) { hi = probe; break; }
+            lo = probe + 1;
+            step <<= 1;
+        }
+        if (lo >= n) return n;
+    } else {
+        hi = g;
+        int step = 1;
+        lo = 0;
+        while (hi > 0) {
+            const int probe = max(hi - step, 0);
+            if (pred(sorted[probe])) { lo = probe + 1; break; }
+            hi = probe;
+            step <<= 1;
+        }
+        if (hi <= 0) return 0;
+    }
+    while (lo < hi) { const int m = (lo + hi) >> 1; if (pred(sorted[m])) lo = m + 1; else hi = m; }
+    return lo;
+}
+
 // window of sorted positions with !(iso < mn) && !(iso > mx)   (intersection.cu:98,107,115)
-__device__ __forceinline__ void iso_window(const float* __restrict__ sorted, int n, float mn, float mx, int& lo, int& hi) {
+// first / scale: sorted[0] and (n - 1) / (sorted[n-1] - sorted[0]) (0 when degenerate) for the interpolation guess.
+__device__ __forceinline__ void iso_window(const float* __restrict__ sorted, int n, float first, float scale, float mn,
+                                           float mx, int& lo, int& hi) {
     if (mn != mn) { lo = 0; hi = n; return; }
-    int a = 0, b = n;
-    while (a < b) { const int m = (a + b) >> 1; if (sorted[m] < mn) a = m + 1; else b = m; }
-    lo = a;
-    b = n;
-    while (a < b) { const int m = (a + b) >> 1; if (!(sorted[m] > mx)) a = m + 1; else b = m; }
-    hi = a;
+    const float gl = (mn - first) * scale, gh = (mx - first) * scale;
+    // float -> int conversion saturates and maps NaN to 0: any value is a valid starting point
+    lo = bound_from_guess(sorted, n, __float2int_ru(gl), [mn](float v) { return v < mn; });
+    hi = bound_from_guess(sorted, n, __float2int_rd(gh) + 1, [mx](float v) { return !(v > mx); });
+    if (hi < lo) hi = lo;
 }
 
 // The three sorted isovalue arrays and their permutations, staged in shared memory per block (a voxel makes ~25
@@ -117,6 +154,7 @@ struct IsoTables {
     const float* sorted[3];
     const int* perm[3];
     int n[3];   // finite isovalues only
+    float first[3], scale[3];   // interpolation guess: position ~ (value - first) * scale
 };
 constexpr int kMaxTableEntries = 6000;   // 48 KB of shared memory; larger isovalue sets are probed in global memory
 
@@ -124,6 +162,12 @@ __device__ __forceinline__ IsoTables load_tables(const IsectWs& w, unsigned char
     IsoTables t;
     const int full[3] = {Ns, N1, N2};
     t.n[0] = w.hdr[4]; t.n[1] = w.hdr[5]; t.n[2] = w.hdr[6];
+    for (int i = 0; i < 3; ++i) {
+        const float a = t.n[i] > 0 ? w.iso_sorted[i][0] : 0.f, b = t.n[i] > 0 ? w.iso_sorted[i][t.n[i] - 1] : 0.f;
+        t.first[i] = a;
+        t.scale[i] = (t.n[i] > 1 && b > a) ? __fdividef((float)(t.n[i] - 1), b - a) : 0.f;
+        if (!(fabsf(t.scale[i]) <= 3.402823466e38f)) t.scale[i] = 0.f;
+    }
     if (Ns + N1 + N2 > kMaxTableEntries) {
         for (int i = 0; i < 3; ++i) { t.sorted[i] = w.iso_sorted[i]; t.perm[i] = w.iso_perm[i]; }
         return t;
@@ -245,11 +289,11 @@ __device__ __forceinline__ Windows voxel_windows(const VoxelFields& f, const Iso
     if (!min_max8(f.a[0], f.a[1], amn, amx)) return r;  // order of intersection.cu:79-91
     if (!min_max8(f.b[0], f.b[1], bmn, bmx)) return r;
     if (!min_max8(f.s[0], f.s[1], smn, smx)) return r;
-    iso_window(w.sorted[1], N1, amn, amx, r.a0, r.a1);
+    iso_window(w.sorted[1], N1, w.first[1], w.scale[1], amn, amx, r.a0, r.a1);
     if (r.a0 >= r.a1) return r;
-    iso_window(w.sorted[2], N2, bmn, bmx, r.b0, r.b1);
+    iso_window(w.sorted[2], N2, w.first[2], w.scale[2], bmn, bmx, r.b0, r.b1);
     if (r.b0 >= r.b1) return r;
-    iso_window(w.sorted[0], Ns, smn, smx, r.s0, r.s1);
+    iso_window(w.sorted[0], Ns, w.first[0], w.scale[0], smn, smx, r.s0, r.s1);
     if (r.s0 >= r.s1) return r;
     r.any = true;
     return r;

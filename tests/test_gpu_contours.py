@@ -280,3 +280,22 @@ def test_intersection_vs_compiled_reference_extension():
     # ours is the lowest-voxel one; both are valid race outcomes
     assert co.intersection_unmatched(s, a, b, si, ai, bi, centers, rm, rp, tol=1e-5) == 0
     assert co.intersection_unmatched(s, a, b, si, ai, bi, centers, m, p, tol=1e-5) == 0
+
+
+def test_intersection_nonuniform_isovalue_sets():
+    """Isovalue sets that defeat the interpolation guess of the window search (clustered, duplicated, far outliers, one or
+    two entries): results stay those of the oracle."""
+    import inf3dp
+    (s, a, b), centers = _grid_fields(14, seed=3)
+    rng = np.random.default_rng(99)
+    si = np.concatenate([rng.uniform(-0.9, 0.9, 20) ** 3, [0.25, 0.25, 0.25, -50.0, 80.0]]).astype(np.float32)
+    rng.shuffle(si)
+    ai = np.concatenate([np.full(3, 0.1), rng.normal(0, 0.02, 9), [1e6]]).astype(np.float32)
+    for bi in (np.array([0.05], np.float32), np.array([-0.3, 0.3], np.float32), np.sort(rng.uniform(-0.8, 0.8, 7)).astype(np.float32)):
+        mo, io, po = co.fields_intersection(s, a, b, si, ai, bi, centers, winner_rule=0)
+        t = [torch.from_numpy(x).cuda() for x in (s, a, b, si, ai, bi, centers)]
+        m, i, p = [x.cpu().numpy() for x in inf3dp.get_fields_intersection_inter_slice(*t)]
+        assert np.array_equal(m, mo) and np.array_equal(i, io)
+        assert np.array_equal(np.isnan(p), np.isnan(po))
+        assert np.nanmax(np.abs(p - po), initial=0.0) <= 1e-6
+        assert m.any()
