@@ -287,6 +287,7 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
         const float* s_misc = reinterpret_cast<const float*>(sptr + C::kSmemMisc);
         float* s_part = reinterpret_cast<float*>(sptr + C::kSmemPart);
         float4* my_stash = stash + (size_t)blockIdx.x * (kStashBytesPerCta / 16) + row;
+        const unsigned long long stash_keep = l2_keep_policy();
         uint32_t a_ready_addr[4];
 #pragma unroll
         for (int r = 0; r < 4; ++r) a_ready_addr[r] = CTAS == 2 ? mapa_rank(bar(C::kBarAReady + r), 0) : bar(C::kBarAReady + r);
@@ -541,7 +542,7 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
                 if (g == 3 || g == 4) {                                   // issue the first stash read under the wait
                     const float4* sp = my_stash + (size_t)(((4 - g) * 16 + grp) * 4) * 128;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) cs[j] = __ldcg(sp + j * 128);
+                    for (int j = 0; j < 4; ++j) cs[j] = ld_keep4(sp + j * 128, stash_keep);
                 }
                 mbar_wait_warp(bar(C::kBarDFull), dphase, lane, pd);
                 dphase ^= 1u;
@@ -582,7 +583,7 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
                             float4* sp = my_stash + (size_t)((g * 16 + m) * 4) * 128;
 #pragma unroll
                             for (int j = 0; j < 4; ++j)
-                                __stcg(sp + j * 128, make_float4(cc[4 * j], cc[4 * j + 1], cc[4 * j + 2], cc[4 * j + 3]));
+                                st_keep4(sp + j * 128, make_float4(cc[4 * j], cc[4 * j + 1], cc[4 * j + 2], cc[4 * j + 3]), stash_keep);
                         } else {
                             // last hidden layer: y += w4 . sin z3 ; start the backward sweep with G w4 (.) cos z3
 #pragma unroll
@@ -606,7 +607,7 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
                         if (mi < 3) {
                             const float4* sp = my_stash + (size_t)(((4 - g) * 16 + m + 4) * 4) * 128;
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) cs[j] = __ldcg(sp + j * 128);
+                            for (int j = 0; j < 4; ++j) cs[j] = ld_keep4(sp + j * 128, stash_keep);
                         }
 #pragma unroll
                         for (int i = 0; i < 16; i += 2) split_pack<true>(gg[i], gg[i + 1], o[i >> 1], o[8 + (i >> 1)]);
