@@ -75,7 +75,8 @@ struct RevCfg {
     static constexpr uint32_t kSmemBias = kSmemW0 + 4096;        // float[3][256]
     static constexpr uint32_t kSmemW4 = kSmemBias + 3072;        // float2[256]
     static constexpr uint32_t kSmemPart = kSmemW4 + 2048;        // float[4 groups][4][128]
-    static constexpr uint32_t kSmemMisc = kSmemPart + 8192;      // inv_scale[3], b4, G, 1/G
+    static constexpr uint32_t kSmemNext = kSmemPart + 8192;      // float[512][3]: the next tile's point, one slot per epilogue thread
+    static constexpr uint32_t kSmemMisc = kSmemNext + 6144;      // inv_scale[3], b4, G, 1/G
     static constexpr uint32_t kSmemBars = kSmemMisc + 64;
     static constexpr int kBarWFull = 0, kBarWEmpty = kStages, kBarAReady = 2 * kStages, kBarDFull = 2 * kStages + 4,
                          kNumBars = 2 * kStages + 5;
@@ -527,9 +528,9 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
             }
         }
         for (int it = 0; it < my_units; ++it) {
-            int64_t npt = 0;                       // the next tile's point (prefetched while this tile's GEMMs run)
-            bool nvalid = false;
-            float nx = 0.f, ny = 0.f, nz = 0.f;
+            // the next tile's point is prefetched while this tile's GEMMs run and parked in this thread's own shared-memory
+            // slot: three registers less across the backward sweep
+            float* s_next = reinterpret_cast<float*>(sptr + C::kSmemNext) + 3 * (grp * 128 + row);
             const bool has_next = it + 1 < my_units;
 
             float acc_y = 0.f, gx = 0.f, gy = 0.f, gz = 0.f;
@@ -538,7 +539,11 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
                 const uint32_t regD = (g & 1) ? regionP : regionQ;
                 const float inv = s_misc[g < 3 ? g : 5 - g];              // 1/S of the layer this GEMM multiplies by
                 float4 cs[4];                                             // stashed cosines of the current slice
-                if (g == 3) load_point(it + 1, npt, nvalid, nx, ny, nz);  // global-load latency hidden behind two GEMMs
+                if (g == 3) {   // global-load latency hidden behind two GEMMs
+                    int64_t npt; bool nvalid; float nx, ny, nz;
+                    load_point(it + 1, npt, nvalid, nx, ny, nz);
+                    s_next[0] = nx; s_next[1] = ny; s_next[2] = nz;
+                }
                 if (g == 3 || g == 4) {                                   // issue the first stash read under the wait
                     const float4* sp = my_stash + (size_t)(((4 - g) * 16 + grp) * 4) * 128;
 #pragma unroll
@@ -623,7 +628,7 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
                             gz = fmaf(g0, w.z, gz);
                         }
                         // these accumulator columns (region P, slice m) are dead now: the next tile's layer 0 goes there
-                        if (has_next) layer0_slice(m, nx, ny, nz, o);
+                        if (has_next) layer0_slice(m, s_next[0], s_next[1], s_next[2], o);
                     }
                     if (g < 5 || has_next) {
                         TC_ST16(addr, o);
@@ -657,7 +662,12 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
             // Hazards into the next unit: the next tile's layer 0 overwrote exactly the accumulator slices this warp had
             // finished reading (tcgen05.wait::ld before the math of each round); s_part is rewritten only after six more
             // d_full phases, which need every epilogue warp (including the readers above) to have passed this point.
-            pt = npt; pvalid = nvalid; px = nx; py = ny; pz = nz;
+            {   // the parked point becomes the current one
+                const int64_t tile = (unit0 + (int64_t)(it + 1) * unit_stride) * CTAS + rank;
+                pt = tile * 128 + row;
+                pvalid = has_next && pt < n;
+                if (has_next) { px = s_next[0]; py = s_next[1]; pz = s_next[2]; }
+            }
         }
         }
         if (dbg && blockIdx.x == 0 && lane == 0) dbg[8 + warp] = wait_d;
