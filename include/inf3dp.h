@@ -124,6 +124,14 @@ int inf3dp_extract_isocontours(const float* vertices, const int32_t* faces, cons
  * the per-isovalue segment counts S_k (the reference's internal pairpoint_nums). */
 int inf3dp_extract_isocontours_status(const void* workspace, int K, int32_t* seg_counts_host,
                                       inf3dp_stream_t stream);
+/* Synchronises `stream` and returns the total number of segments the last call that used `workspace` produced (or
+ * would have produced: after INF3DP_EOVERFLOW this is the pool size to pass to
+ * inf3dp_extract_isocontours_workspace_bytes_segments for the retry); -1 on a CUDA error. */
+int64_t inf3dp_extract_isocontours_required_segments(const void* workspace, int K, inf3dp_stream_t stream);
+/* Threading: the dense entry point forks its zero fill and its chain onto ONE internal, process-wide, highest-priority
+ * helper stream per device (created on first use) and joins it back into `stream` before returning, on every exit path;
+ * the fork / join events come from an internal pool.  Concurrent calls on different streams are safe (their chains
+ * serialise on the helper stream); the compact entry point uses `stream` only. */
 
 /* Compact variant: the same row streams without the dense zero-padded [K, nF, 3] contract.
  * Isovalue k's rows (loops separated and terminated by (-1e9,-1e9,-1e9) rows, exactly the first row_counts[k] rows of

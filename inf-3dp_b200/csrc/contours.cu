@@ -973,6 +973,57 @@ int get_side_stream(cudaStream_t* out) {
     return INF3DP_OK;
 }
 
+// Fork / join of the caller's stream and the helper stream.  The two events come from a small per-process pool (no
+// cudaEventCreate / Destroy per call) and go back to it on EVERY exit path; if the call fails after the fork, the
+// destructor still joins the helper stream into the caller's stream, so an error never leaves the two streams unordered.
+static std::vector<cudaEvent_t> g_event_pool;
+
+cudaEvent_t pool_get_event() {
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
+    }
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return e;
+}
+
+void pool_put_event(cudaEvent_t e) {
+    if (!e) return;
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_event_pool.size() < 64) g_event_pool.push_back(e); else cudaEventDestroy(e);
+}
+
+struct ForkJoin {
+    cudaStream_t main_ = nullptr, side_ = nullptr;
+    cudaEvent_t fork_ = nullptr, join_ = nullptr;
+    bool forked = false, joined = false;
+    ForkJoin(cudaStream_t m, cudaStream_t s) : main_(m), side_(s), fork_(pool_get_event()), join_(pool_get_event()) {}
+    bool ok() const { return fork_ && join_; }
+    cudaError_t fork() {
+        cudaError_t e = cudaEventRecord(fork_, main_);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(side_, fork_, 0);
+        forked = (e == cudaSuccess);
+        return e;
+    }
+    cudaError_t join() {
+        cudaError_t e = cudaEventRecord(join_, side_);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(main_, join_, 0);
+        joined = true;
+        return e;
+    }
+    ~ForkJoin() {
+        if (forked && !joined) join();
+        pool_put_event(fork_);
+        pool_put_event(join_);
+    }
+};
+
+// The face kernels keep the K sorted isovalues and their permutation in dynamic shared memory (8 K bytes): above the
+// 48 KB default (K > 6144; the ABI accepts K <= 12000 = 96 KB) the kernel has to be opted in.
+template <bool EMIT>
+int faces_smem_opt_in(size_t fsmem);
+
 // Largest pool that fits the caller's workspace (>= the default, doubling).
 // Zero fill of the whole dense contract (12 K F bytes), independent of every other kernel of the call: it starts at t = 0
 // on the caller's stream while the chain runs on the helper stream.  Many short blocks (see contour_fill_kernel).
@@ -1020,6 +1071,13 @@ __global__ void contour_export_kernel(int K, ContourWs w, long long* __restrict_
         row_offsets[k] = 2ll * w.seg_offset[k];
         row_counts[k] = w.hdr[0] != 0 ? 0 : w.rows_used[k];
     }
+}
+
+template <bool EMIT>
+int faces_smem_opt_in(size_t fsmem) {
+    if (fsmem > 48 * 1024)
+        INF3DP_CUDA(cudaFuncSetAttribute(contour_faces_kernel<EMIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+    return INF3DP_OK;
 }
 
 int fit_capacity(int nF, int K, size_t ws_bytes) {
@@ -1080,17 +1138,18 @@ int inf3dp_extract_isocontours(const float* V, const int32_t* F, const float* fi
     mark(0, st);
 
     const int sms = num_sms();
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    INF3DP_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
-    INF3DP_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    const size_t fsmem = (size_t)K * 8;
+    if ((rc = faces_smem_opt_in<false>(fsmem)) != INF3DP_OK) return rc;
+    if ((rc = faces_smem_opt_in<true>(fsmem)) != INF3DP_OK) return rc;
+    ForkJoin fj(st, side);     // joins and returns its events to the pool on every exit path
+    if (!fj.ok()) { set_error("extract_isocontours: cudaEventCreate failed"); return INF3DP_ECUDA; }
     w.defer = 1;
 
     // fork at t = 0.  Helper stream (highest priority): the whole latency-bound chain prep -> count -> scan -> hash
     // clear -> emit -> link -> walk, which only RECORDS the row order of every isovalue.  Caller's stream: the zero fill
     // of the dense contract, which depends on nothing.  Join, then the recorded rows are scattered over the zeros.
-    INF3DP_CUDA(cudaEventRecord(ev_fork, st));
+    INF3DP_CUDA(fj.fork());
     mark(1, st);
-    INF3DP_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
     // (the fill is enqueued first: seven chain launches cost ~30 us of host time that it would otherwise wait for)
     mark(2, st);
     if (nF > 0 && dev_skip != 1) {
@@ -1105,7 +1164,6 @@ int inf3dp_extract_isocontours(const float* V, const int32_t* F, const float* fi
         INF3DP_LAUNCH_CHECK("contour_fill_all_kernel");
     }
     const int fblocks = (nF + kFaceThreads - 1) / kFaceThreads;
-    const size_t fsmem = (size_t)K * 8;
     if (dev_skip != 2) {
         contour_prep_kernel<<<1, 1024, 0, side>>>(iso, K, w);
         INF3DP_LAUNCH_CHECK("contour_prep_kernel");
@@ -1128,19 +1186,15 @@ int inf3dp_extract_isocontours(const float* V, const int32_t* F, const float* fi
         INF3DP_CUDA(launch_walk(nF, K, w, merged, nums, side));
         INF3DP_LAUNCH_CHECK("contour_walk_kernel");
     }
-    INF3DP_CUDA(cudaEventRecord(ev_join, side));
     mark(6, side);
-
     mark(3, st);
-    INF3DP_CUDA(cudaStreamWaitEvent(st, ev_join, 0));  // join
+    INF3DP_CUDA(fj.join());
     if (nF > 0 && dev_skip != 2) {
         dim3 grid(8, K);
         contour_scatter_kernel<<<grid, 256, 0, st>>>(nF, K, w, merged);
         INF3DP_LAUNCH_CHECK("contour_scatter_kernel");
     }
     mark(7, st);
-    INF3DP_CUDA(cudaEventDestroy(ev_fork));
-    INF3DP_CUDA(cudaEventDestroy(ev_join));
     if (debug) {
         cudaStreamSynchronize(st);
         float t[8] = {0};
@@ -1192,10 +1246,15 @@ int inf3dp_extract_isocontours_compact(const float* V, const int32_t* F, const f
                      "(inf3dp_extract_isocontours_compact_rows)", (long long)rows_capacity, 2ll * w.cap);
     w.compact = 1;
     cudaStream_t st = (cudaStream_t)stream;
+    const size_t fsmem = (size_t)K * 8;
+    {
+        int rc = faces_smem_opt_in<false>(fsmem);
+        if (rc == INF3DP_OK) rc = faces_smem_opt_in<true>(fsmem);
+        if (rc != INF3DP_OK) return rc;
+    }
     contour_prep_kernel<<<1, 1024, 0, st>>>(iso, K, w);
     INF3DP_LAUNCH_CHECK("contour_prep_kernel");
     const int fblocks = (nF + kFaceThreads - 1) / kFaceThreads;
-    const size_t fsmem = (size_t)K * 8;
     if (fblocks > 0) {
         contour_faces_kernel<false><<<fblocks, kFaceThreads, fsmem, st>>>(V, F, fields, nV, nF, K, w);
         INF3DP_LAUNCH_CHECK("contour_faces_kernel<count>");
@@ -1216,6 +1275,16 @@ int inf3dp_extract_isocontours_compact(const float* V, const int32_t* F, const f
     contour_export_kernel<<<(K + 255) / 256, 256, 0, st>>>(K, w, (long long*)row_offsets, row_counts);
     INF3DP_LAUNCH_CHECK("contour_export_kernel");
     return INF3DP_OK;
+}
+
+int64_t inf3dp_extract_isocontours_required_segments(const void* ws, int K, inf3dp_stream_t stream) {
+    if (ws == nullptr || K <= 0) return 0;
+    ContourWs w = carve(const_cast<void*>(ws), K, 1024);
+    int hdr[4] = {0, 0, 0, 0};
+    cudaStream_t st = (cudaStream_t)stream;
+    if (cudaMemcpyAsync(hdr, w.hdr, sizeof(hdr), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return (int64_t)hdr[1];
 }
 
 int inf3dp_extract_isocontours_status(const void* ws, int K, int32_t* seg_counts_host, inf3dp_stream_t stream) {

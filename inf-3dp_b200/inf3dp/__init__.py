@@ -17,11 +17,20 @@ from .collision import (CollTVSDF, collision_evaluation, tvsdf_collision_forward
                         transform_nozzle_pcd_with_quaternion)
 
 
-def patch_reference():
+def patch_reference(force=False):
     """Rebind the reference's hot-path classes in already-imported reference modules:
     `modules.SingleBVPNet` -> inf3dp.SingleBVPNet.  `diff_operators` is left untouched: its autograd calls work on
-    the fused outputs."""
+    the fused outputs.
+
+    The drop-in is inference-only (no gradient path to the weights).  When the calling process has imported the
+    reference's `training` module -- i.e. it is a training script -- rebinding the class would make the networks it is
+    about to train untrainable, so this raises unless force=True (e.g. train_collision.py, which trains the quaternion
+    network against FROZEN field networks: rebind by hand for those instead)."""
     import sys
+    if not force and "training" in sys.modules and hasattr(sys.modules["training"], "train"):
+        raise RuntimeError("inf3dp.patch_reference(): the reference's `training` module is imported -- this looks like a "
+                           "training script, and inf3dp.SingleBVPNet is inference-only (weights get no gradients).  "
+                           "Keep modules.SingleBVPNet for the networks being trained; pass force=True to rebind anyway.")
     m = sys.modules.get("modules")
     if m is not None:
         m.SingleBVPNet = SingleBVPNet

@@ -37,6 +37,7 @@ SIGNATURES = {
     "inf3dp_extract_isocontours_workspace_bytes_segments": (_sz, [_i, _i, _i, _i64]),
     "inf3dp_extract_isocontours": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "inf3dp_extract_isocontours_status": (_i, [_vp, _i, _vp, _vp]),
+    "inf3dp_extract_isocontours_required_segments": (_i64, [_vp, _i, _vp]),
     "inf3dp_extract_isocontours_compact_rows": (_i64, [_i, _i, _i, _sz]),
     "inf3dp_extract_isocontours_compact": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
     "inf3dp_fields_intersection_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),

@@ -28,7 +28,11 @@ def _check_input(t, name, dtype=None):
 
 
 def extract_isocontours_raw(vertices, faces, fields, iso_values, sync=True, want_seg_counts=False):
-    """-> contours_merged [K,F,3] f32, contour_nums [K] i32 (, seg_counts [K] i32 on the host)."""
+    """-> contours_merged [K,F,3] f32, contour_nums [K] i32 (, seg_counts [K] i32 on the host).
+
+    sync=False returns without reading the status back: a segment-pool overflow (coarse mesh with a dense isovalue set:
+    more than nF + 65536 segments) is then NOT detected and the call yields all-zero contours with contour_nums == 0;
+    use it only where the pool is known to suffice (benchmarks), never on user data."""
     _check_input(vertices, "vertices", torch.float32)
     _check_input(faces, "faces", torch.int32)
     _check_input(fields, "fields", torch.float32)
@@ -57,8 +61,9 @@ def extract_isocontours_raw(vertices, faces, fields, iso_values, sync=True, want
                 break
             rc = L.inf3dp_extract_isocontours_status(_lib.ptr(ws), K, seg_host, st)
             if rc == _lib.EOVERFLOW and attempt == 0:
-                # the segment pool was too small for this mesh/field: size it for the worst case and retry once
-                ws_bytes = L.inf3dp_extract_isocontours_workspace_bytes_segments(nV, nF, K, int(nF) * int(K))
+                # the segment pool was too small for this mesh/field: the count pass knows how many segments there are
+                need = L.inf3dp_extract_isocontours_required_segments(_lib.ptr(ws), K, st)
+                ws_bytes = L.inf3dp_extract_isocontours_workspace_bytes_segments(nV, nF, K, need if need > 0 else int(nF) * int(K))
                 continue
             _lib.check(rc)
             break
@@ -100,7 +105,8 @@ def extract_isocontours_compact(vertices, faces, fields, iso_values):
                                                             ws_bytes, st))
             rc = L.inf3dp_extract_isocontours_status(_lib.ptr(ws), K, None, st)
             if rc == _lib.EOVERFLOW and attempt == 0:
-                ws_bytes = L.inf3dp_extract_isocontours_workspace_bytes_segments(nV, nF, K, int(nF) * int(K))
+                need = L.inf3dp_extract_isocontours_required_segments(_lib.ptr(ws), K, st)
+                ws_bytes = L.inf3dp_extract_isocontours_workspace_bytes_segments(nV, nF, K, need if need > 0 else int(nF) * int(K))
                 continue
             _lib.check(rc)
             break

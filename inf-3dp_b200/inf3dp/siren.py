@@ -184,6 +184,28 @@ class FusedSirenMixin:
 
     lazy_jacobian = False  # True: forward computes values only and the Jacobian is launched on demand in backward
 
+    # ---- inference only, and loud about it --------------------------------------------------------------------------
+    # The fused kernels treat the weights as constants: there is no autograd path from the outputs to the parameters.
+    # In a reference training loop loss.backward() would still succeed (the coordinates are a leaf), every parameter's
+    # .grad would stay None and optimizer.step() would silently do nothing.  So: parameters are created frozen,
+    # train(True) raises, and forward() raises if someone re-enabled requires_grad on a parameter.
+    def _freeze(self):
+        for p in self.parameters():
+            p.requires_grad_(False)
+
+    def train(self, mode: bool = True):
+        if mode:
+            raise RuntimeError(f"inf3dp.{type(self).__name__} is inference-only: the fused kernels have no gradient path to "
+                               "the weights, a training loop on it would silently not train.  Train with the reference's "
+                               "modules.SingleBVPNet / MLPClassifier and load the state_dict here (same keys); call .eval() "
+                               "on this module (the reference's query helpers do, utils.py:146,228).")
+        return super().train(False)
+
+    def _assert_frozen(self):
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise RuntimeError(f"inf3dp.{type(self).__name__}: a parameter has requires_grad=True, but gradients only flow to "
+                               "the coordinates (inference-only drop-in); weight gradients would silently stay None")
+
     def _jet(self, flat_x, order, mode=None):
         ws, bs = self._weights()
         blob = self._packed.get(ws, bs)
@@ -250,6 +272,8 @@ class SingleBVPNet(FusedSirenMixin, nn.Module):
                     nn.init.kaiming_normal_(seq[0].weight, a=0.0, nonlinearity="relu", mode="fan_in")
         act = _lib.ACT_SINE if type == "sine" else _lib.ACT_RELU
         self._packed = PackedWeights(in_features, hidden_features, num_hidden_layers, out_features, act, 30.0)
+        self._freeze()
+        nn.Module.train(self, False)
 
     def _weights(self):
         lins = [seq[0] for seq in self.net.net]
@@ -258,6 +282,7 @@ class SingleBVPNet(FusedSirenMixin, nn.Module):
     def forward(self, model_input, params=None):
         if params is not None:
             raise NotImplementedError("inf3dp.SingleBVPNet: hypernetwork `params` are not supported (inference path)")
+        self._assert_frozen()
         coords_org = model_input["coords"].clone().detach().requires_grad_(True)  # modules.py:148
         eager = torch.is_grad_enabled() and not self.lazy_jacobian
         out = _SirenValue.apply(coords_org, self, eager)
@@ -273,12 +298,15 @@ class MLPClassifier(FusedSirenMixin, nn.Module):
                                      nn.ReLU(), nn.Linear(hidden_dim, num_classes))
         self.out_features = int(num_classes)
         self._packed = PackedWeights(input_dim, hidden_dim, 1, num_classes, _lib.ACT_RELU, 1.0)
+        self._freeze()
+        nn.Module.train(self, False)
 
     def _weights(self):
         lins = [self.network[0], self.network[2], self.network[4]]
         return [l.weight for l in lins], [l.bias for l in lins]
 
     def forward(self, x):
+        self._assert_frozen()
         flat = x.reshape(-1, x.shape[-1])
         y, _, _ = self._jet(flat, 0)
         return y.view(*x.shape[:-1], self.out_features)

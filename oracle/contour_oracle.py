@@ -94,44 +94,10 @@ def intersection_unmatched(slice_f, l1_f, l2_f, s_iso, l1_iso, l2_iso, centers, 
         len(bi), _p(m, ctypes.c_uint8), _p(p, ctypes.c_float), ctypes.c_float(tol)))
 
 
-# ---- helpers shared by tests and bench (synthetic inputs of SURVEY.md section 8d, cfg 3) -----------------
-
-def torus_mesh(nu, nv, R=0.6, r=0.3, jitter=1e-4, seed=0):
-    """Closed UV-torus, nu*nv quads split into 2 triangles each -> V [nu*nv,3] f32, F [2*nu*nv,3] i32."""
-    rng = np.random.default_rng(seed)
-    u = np.arange(nu) * (2 * np.pi / nu)
-    v = np.arange(nv) * (2 * np.pi / nv)
-    uu, vv = np.meshgrid(u, v, indexing="ij")
-    x = (R + r * np.cos(vv)) * np.cos(uu)
-    y = (R + r * np.cos(vv)) * np.sin(uu)
-    z = r * np.sin(vv)
-    V = np.stack([x, y, z], -1).reshape(-1, 3)
-    V = V + rng.normal(0.0, jitter, V.shape)
-    i = np.arange(nu)[:, None]
-    j = np.arange(nv)[None, :]
-    a = (i * nv + j).ravel()
-    b = (((i + 1) % nu) * nv + j).ravel()
-    c = (((i + 1) % nu) * nv + (j + 1) % nv).ravel()
-    d = (i * nv + (j + 1) % nv).ravel()
-    F = np.concatenate([np.stack([a, b, c], -1), np.stack([a, c, d], -1)], 0)
-    # interleave the two triangles of each quad so neighbouring faces stay close in index
-    F = F.reshape(2, -1, 3).transpose(1, 0, 2).reshape(-1, 3)
-    return V.astype(np.float32), F.astype(np.int32)
-
-
-def split_rows(merged_k, num):
-    """Split one isovalue's row stream at the -1e9 separator rows (toolpath_utils.py:65-82) -> list of [n,3]."""
-    sep = np.where(merged_k[:, 0] < -1e2)[0]
-    out, start = [], 0
-    for s in sep[:num] if num is not None else sep:
-        out.append(merged_k[start:s])
-        start = s + 1
-    return out
-
-
-def rows_used(merged_k, num):
-    """S_k + C_k recovered from the dense stream: index of the last separator + 1."""
-    if num == 0:
-        return 0
-    sep = np.where(merged_k[:, 0] < -1e2)[0]
-    return int(sep[num - 1]) + 1
+# ---- synthetic inputs / row-stream helpers: they live in the product package's test-support module (bench.py's product
+# arm uses them too and must not import oracle/); re-exported here for the tests that already use co.torus_mesh etc.
+import sys as _sys
+_PKG = os.path.join(os.path.dirname(_HERE), "inf-3dp_b200")
+if _PKG not in _sys.path:
+    _sys.path.insert(0, _PKG)
+from inf3dp.testing import torus_mesh, split_rows, rows_used  # noqa: E402,F401

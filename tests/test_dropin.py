@@ -66,3 +66,35 @@ def test_qupkg_and_dropin_modules_resolve():
         sys.path.pop(0)
         for n in ("modules", "diff_operators"):
             sys.modules.pop(n, None)
+
+
+def test_dropin_is_loudly_inference_only():
+    """a reference training loop on the drop-in must not silently 'train' (weights get no gradients)."""
+    import sys
+    import types
+    import inf3dp
+    net = inf3dp.SingleBVPNet(type="sine", in_features=3)
+    assert not net.training and not any(p.requires_grad for p in net.parameters())
+    net.eval()
+    with pytest.raises(RuntimeError, match="inference-only"):
+        net.train()
+    holder = torch.nn.Sequential(net)
+    with pytest.raises(RuntimeError, match="inference-only"):
+        holder.train()
+    lvl = inf3dp.MLPClassifier(num_classes=3)
+    with pytest.raises(RuntimeError, match="inference-only"):
+        lvl.train()
+    net.net.net[0][0].weight.requires_grad_(True)
+    with pytest.raises(RuntimeError, match="requires_grad"):
+        net({"coords": torch.zeros(2, 3)})
+    fake = types.ModuleType("training")
+    fake.train = lambda *a, **k: None
+    sys.modules["training"] = fake
+    sys.modules.setdefault("modules", types.ModuleType("modules"))
+    try:
+        with pytest.raises(RuntimeError, match="training script"):
+            inf3dp.patch_reference()
+        assert inf3dp.patch_reference(force=True) is True
+    finally:
+        sys.modules.pop("training", None)
+        sys.modules.pop("modules", None)
