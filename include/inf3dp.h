@@ -97,6 +97,19 @@ int inf3dp_unit_normals(const float* grad, int64_t n, float eps, float* normals,
 int inf3dp_siren_value_grad_rows(const void* packed, const float* x, int64_t n, float* rows, void* workspace,
                                  size_t workspace_bytes, inf3dp_stream_t stream);
 int inf3dp_unit_normals_rows(const float* rows, int64_t n, float eps, float* normals, inf3dp_stream_t stream);
+/* The same query FUSED WITH THE MULTI-GPU ALL-GATHER of its rows (points sharded, weights replicated,
+ * one final all-gather -- the reference has no distributed code).  The engine's epilogue stores every row directly into
+ * the gathered buffers of the ranks of the job, over NVLink, tile by tile while the tensor cores work on the next tile:
+ *   multicast_rows != NULL  one multimem.st per point to an NVLink multicast address (the NVSwitch replicates it to every
+ *                           rank, this one included); peer_rows is ignored
+ *   otherwise               one 16-byte store per point and peer to each of peer_rows[0..n_peers) (1 <= n_peers <= 8;
+ *                           HOST array of peer-mapped DEVICE pointers, e.g. CUDA IPC / symmetric-memory mappings)
+ * Each pointer addresses the destination of row 0 of THIS launch (the caller applies rank and chunk offsets).  The
+ * rows become visible to the other ranks after this launch has completed AND the ranks have synchronised (any
+ * cross-rank barrier with system-scope release/acquire on the same stream); no SM is set aside for a communication kernel. */
+int inf3dp_siren_value_grad_rows_peers(const void* packed, const float* x, int64_t n, float* const* peer_rows, int n_peers,
+                                       float* multicast_rows, void* workspace, size_t workspace_bytes,
+                                       inf3dp_stream_t stream);
 
 /* Curvature tail.  Replaces the per-point Python loop of diff_operators.py:167-220 (min_max_curvs_and_vectors)
  * and construct_tangent_basis (:280-298): grad [n,3], hess [n,3,3] -> kappa [n,2] (min,max), dirs [n,2,3]. */

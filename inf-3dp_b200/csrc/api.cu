@@ -310,6 +310,21 @@ int inf3dp_siren_value_grad_rows(const void* packed, const float* x, int64_t n, 
     return siren_rev_launch_rows(packed, h, x, n, rows, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
+int inf3dp_siren_value_grad_rows_peers(const void* packed, const float* x, int64_t n, float* const* peer_rows, int n_peers,
+                                       float* multicast_rows, void* workspace, size_t workspace_bytes,
+                                       inf3dp_stream_t stream) {
+    INF3DP_CHECK_ARG(packed != nullptr, "siren_value_grad_rows_peers: null packed weights");
+    INF3DP_CHECK_ARG(n >= 0, "siren_value_grad_rows_peers: negative point count");
+    if (n == 0) return INF3DP_OK;
+    INF3DP_CHECK_ARG(x != nullptr, "siren_value_grad_rows_peers: null x");
+    SirenHeader h;
+    int rc = lookup_header(packed, &h);
+    if (rc != INF3DP_OK) return rc;
+    INF3DP_CHECK_ARG(h.rev_ok, "siren_value_grad_rows_peers: needs a single-output sine network 3-256-256-256-256-1");
+    return siren_rev_launch_rows_peers(packed, h, x, n, peer_rows, n_peers, multicast_rows, workspace, workspace_bytes,
+                                       (cudaStream_t)stream);
+}
+
 int inf3dp_unit_normals_rows(const float* rows, int64_t n, float eps, float* normals, inf3dp_stream_t stream) {
     INF3DP_CHECK_ARG(n >= 0, "unit_normals_rows: negative n");
     if (n == 0) return INF3DP_OK;

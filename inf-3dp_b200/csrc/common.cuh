@@ -145,6 +145,8 @@ int siren_rev_launch(const void* packed, const SirenHeader& h, const float* x, i
                      size_t ws_bytes, cudaStream_t stream);
 int siren_rev_launch_rows(const void* packed, const SirenHeader& h, const float* x, int64_t n, float* rows, void* ws,
                           size_t ws_bytes, cudaStream_t stream);
+int siren_rev_launch_rows_peers(const void* packed, const SirenHeader& h, const float* x, int64_t n, float* const* peer_rows,
+                                int n_peers, float* multicast_rows, void* ws, size_t ws_bytes, cudaStream_t stream);
 int siren_mlp_pack(const float* const* W, const float* const* b, int out_features, void* packed, const SirenLayout& lay,
                    SirenHeader& hdr, cudaStream_t stream);
 int siren_mlp_launch(const void* packed, const SirenHeader& h, const float* x, int64_t n, float* y, cudaStream_t stream);

@@ -14,7 +14,6 @@
 //   * inf3dp_fields_intersection_grid reads the three [N,N,N] sample grids directly: the reference's host-side
 //     8x corner expansion (toolpath_utils.py:986-1019) and voxel-centre tensor (:1021-1033) are never built
 #include <algorithm>
-#include <cstdlib>
 
 #include "common.cuh"
 
@@ -25,9 +24,7 @@ struct IsectWs {
     int* hdr;         // [4..6] finite isovalue counts (slice, l1, l2)
     float* iso_sorted[3];
     int* iso_perm[3];
-    int* winner;      // [cells]  (fused path: unsigned, 0xffffffff = no voxel yet)
-    unsigned* ctrl;   // fused path: [0] tile ticket, [1] known done-prefix, [4 + i] done bits of tiles 32 i .. 32 i + 31
-    size_t winner_bytes, ctrl_bytes;
+    int* winner;      // [cells]
     size_t total_bytes;
 };
 
@@ -42,45 +39,57 @@ IsectWs carve_isect(void* base, long long voxels, long long cells, int Ns, int N
         w.iso_sorted[i] = (float*)(b + take((size_t)(n[i] > 0 ? n[i] : 1) * 4));
         w.iso_perm[i] = (int*)(b + take((size_t)(n[i] > 0 ? n[i] : 1) * 4));
     }
-    w.winner_bytes = (size_t)cells * 4;
-    w.winner = (int*)(b + take(w.winner_bytes));
-    const long long n_tiles = (voxels + 255) / 256;
-    w.ctrl_bytes = (size_t)(4 + (n_tiles + 31) / 32 + 1) * 4;
-    w.ctrl = (unsigned*)(b + take(w.ctrl_bytes));
+    w.winner = (int*)(b + take((size_t)cells * 4));
+    (void)voxels;
     w.total_bytes = o;
     return w;
 }
 
-// Rank sort (ties keep input order).  NaN isovalues are parked behind the finite ones and never searched:
-// a NaN isovalue is ignored here (the reference would let it hit every voxel, intersection.cu:98 -- a
-// documented divergence on meaningless input).
+// Rank sort (ties keep input order), one WARP per element: the lanes split the comparison loop and reduce with
+// shuffles (a thread per element made the prep kernel 20 us long at Ns = 500).  NaN isovalues are parked behind the
+// finite ones and never searched: a NaN isovalue is ignored here (the reference would let it hit every voxel,
+// intersection.cu:98 -- a documented divergence on meaningless input).
 __device__ __forceinline__ void rank_sort(const float* __restrict__ iso, int n, float* sorted, int* perm, int* n_finite) {
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int i = warp; i < n; i += nwarps) {
         const float vi = iso[i];
-        int rank = 0;
-        if (vi == vi) {
-            for (int j = 0; j < n; ++j) { const float vj = iso[j]; rank += (vj < vi) || (vj == vi && j < i); }
-        } else {
-            int nn = 0, before = 0;
-            for (int j = 0; j < n; ++j) { const float vj = iso[j]; nn += (vj == vj); before += (vj != vj) && j < i; }
-            rank = nn + before;
+        int less = 0, finite = 0, nan_before = 0;
+        for (int j = lane; j < n; j += 32) {
+            const float vj = iso[j];
+            less += (vj < vi) || (vj == vi && j < i);
+            finite += (vj == vj);
+            nan_before += (vj != vj) && j < i;
         }
-        sorted[rank] = vi;
-        perm[rank] = i;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            less += __shfl_xor_sync(0xffffffffu, less, o);
+            finite += __shfl_xor_sync(0xffffffffu, finite, o);
+            nan_before += __shfl_xor_sync(0xffffffffu, nan_before, o);
+        }
+        if (lane == 0) {
+            const int rank = (vi == vi) ? less : finite + nan_before;
+            sorted[rank] = vi;
+            perm[rank] = i;
+            if (i == 0) *n_finite = finite;
+        }
     }
-    if (threadIdx.x == 0) {
-        int nn = 0;
-        for (int j = 0; j < n; ++j) nn += (iso[j] == iso[j]);
-        *n_finite = nn;
-    }
+    if (n == 0 && threadIdx.x == 0) *n_finite = 0;
 }
 
+// One block per isovalue array (the three rank sorts run side by side; each stages its array in shared memory).
 __global__ void isect_prep_kernel(const float* s_iso, const float* a_iso, const float* b_iso, int Ns, int N1, int N2,
                                   IsectWs w) {
-    if (threadIdx.x < 4) w.hdr[threadIdx.x] = 0;
-    rank_sort(s_iso, Ns, w.iso_sorted[0], w.iso_perm[0], &w.hdr[4]);
-    rank_sort(a_iso, N1, w.iso_sorted[1], w.iso_perm[1], &w.hdr[5]);
-    rank_sort(b_iso, N2, w.iso_sorted[2], w.iso_perm[2], &w.hdr[6]);
+    extern __shared__ float s_prep[];
+    const int which = blockIdx.x;
+    const float* iso = which == 0 ? s_iso : (which == 1 ? a_iso : b_iso);
+    const int n = which == 0 ? Ns : (which == 1 ? N1 : N2);
+    if (which == 0 && threadIdx.x < 4) w.hdr[threadIdx.x] = 0;
+    const bool staged = n <= 8192;
+    if (staged) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) s_prep[i] = iso[i];
+        __syncthreads();
+    }
+    rank_sort(staged ? s_prep : iso, n, w.iso_sorted[which], w.iso_perm[which], &w.hdr[4 + which]);
 }
 
 // Winner initialisation (the outputs are initialised by the cell kernel).
@@ -346,175 +355,11 @@ isect_elect_kernel(const FieldSrc src, long long voxels, int Ns, int N1, int N2,
 constexpr unsigned long long kEdgeC1 = 0x321065442100ull;   // first corner of edge e in bits [4e, 4e+4)
 constexpr unsigned long long kEdgeC2 = 0x765477653321ull;   // second corner
 
-// intersection.cu:135-160: sum of the edge-crossing points of one field, inclusive edge test, unguarded division.
-// The 12 inclusive tests are evaluated branch-free into a mask; only the crossing edges (typically 3-6) then pay for the
-// division and the interpolation, in ascending edge order (the reference's summation order).  `sv` = this thread's
-// eight corner values in shared memory (stride kCellThreads), lo / hi = the two corner coordinates per axis.
-constexpr int kCellThreads = 256;
-__device__ __forceinline__ int edge_sum(const float4 c_lo, const float4 c_hi, const float* sv, float iso, const float* lo,
-                                        const float* hi, float* acc) {
-    const float v[8] = {c_lo.x, c_lo.y, c_lo.z, c_lo.w, c_hi.x, c_hi.y, c_hi.z, c_hi.w};
-    unsigned mask = 0;
-#pragma unroll
-    for (int e = 0; e < 12; ++e) {
-        const float a = v[(kEdgeC1 >> (4 * e)) & 15], b = v[(kEdgeC2 >> (4 * e)) & 15];
-        mask |= (iso >= fminf(a, b) && iso <= fmaxf(a, b)) ? (1u << e) : 0u;
-    }
-    const int cnt = __popc(mask);
-    acc[0] = acc[1] = acc[2] = 0.f;
-    while (mask) {
-        const int e = __ffs(mask) - 1;
-        mask &= mask - 1;
-        const int c1 = (int)((kEdgeC1 >> (4 * e)) & 15), c2 = (int)((kEdgeC2 >> (4 * e)) & 15);
-        const float a = sv[c1 * kCellThreads], b = sv[c2 * kCellThreads];
-        const float t = __fdiv_rn(iso - a, b - a);
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-            const float x1 = ((c1 >> d) & 1) ? hi[d] : lo[d];
-            const float x2 = ((c2 >> d) & 1) ? hi[d] : lo[d];
-            acc[d] += fmaf(t, x2 - x1, x1);
-        }
-    }
-    return cnt;
-}
-
-// pass 2, cell centric: one thread per cell.  A cell without a winner gets the "nothing here" outputs (mask 0,
-// indices -1, point 0: no separate initialisation pass); otherwise the cell's winner voxel is re-read (96 B of corner
-// fields + its centre) and the three edge sums are evaluated for exactly this cell's isovalues.  Uniform work per
-// thread, no index windows.  A block covers 8 consecutive slice isovalues x 32 consecutive lattice-2 isovalues of one
-// lattice-1 isovalue: every warp writes 32 consecutive cells (coalesced rows), and the 8 warps mostly re-read the SAME
-// winner voxels (a voxel typically spans 2-3 neighbouring slice isovalues), which the L1 serves.
-constexpr int kCellTileS = 8, kCellTile2 = 32;
-
-template <bool GRID>
-__global__ void __launch_bounds__(256)
-isect_cell_kernel(const FieldSrc src, const float* __restrict__ s_iso, const float* __restrict__ a_iso,
-                  const float* __restrict__ b_iso, int Dx, int Ns, int N1, int N2, long long tiles, IsectWs w,
-                  uint8_t* __restrict__ mask, int16_t* __restrict__ idx, float* __restrict__ pts) {
-    __shared__ float s_corner[3 * 8 * kCellThreads];   // [field][corner][thread]
-    const float vs = (float)(2.0 / (double)(float)Dx);  // intersection.cu:54
-    const int tiles2 = (N2 + kCellTile2 - 1) / kCellTile2;
-    const int r = threadIdx.x >> 5, q = threadIdx.x & 31;
-    for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
-        const int t2 = (int)(t % tiles2);
-        const long long u = t / tiles2;
-        const int i1 = (int)(u % N1);
-        const int ts = (int)(u / N1);
-        const int is = ts * kCellTileS + r, i2 = t2 * kCellTile2 + q;
-        if (is >= Ns || i2 >= N2) continue;
-        const long long c = ((long long)is * N1 + i1) * N2 + i2;
-        const int v = __ldcs(&w.winner[c]);
-        if (v == 0x7fffffff) {
-            mask[c] = 0;
-            idx[3 * c] = -1; idx[3 * c + 1] = -1; idx[3 * c + 2] = -1;
-            pts[3 * c] = 0.f; pts[3 * c + 1] = 0.f; pts[3 * c + 2] = 0.f;
-            continue;
-        }
-        VoxelFields f;
-        load_voxel<GRID, false>(src, v, f);
-        float ctr[3];
-        load_center<GRID>(src, v, ctr);
-        // corner coordinates: centre + voxel_size * (-0.5 | +0.5), the two values per axis shared by all three fields
-        float lo[3], hi[3];
-#pragma unroll
-        for (int d = 0; d < 3; ++d) { lo[d] = fmaf(vs, -0.5f, ctr[d]); hi[d] = fmaf(vs, 0.5f, ctr[d]); }
-        float* sv = s_corner + threadIdx.x;
-        auto stage = [&](int fi, const float4 a, const float4 b) {
-            float* q = sv + fi * 8 * kCellThreads;
-            q[0] = a.x; q[kCellThreads] = a.y; q[2 * kCellThreads] = a.z; q[3 * kCellThreads] = a.w;
-            q[4 * kCellThreads] = b.x; q[5 * kCellThreads] = b.y; q[6 * kCellThreads] = b.z; q[7 * kCellThreads] = b.w;
-        };
-        stage(0, f.a[0], f.a[1]); stage(1, f.b[0], f.b[1]); stage(2, f.s[0], f.s[1]);   // read back by this thread only
-        float pa[3], pb[3], ps[3];
-        const int ca = edge_sum(f.a[0], f.a[1], sv, a_iso[i1], lo, hi, pa);
-        const int cb = edge_sum(f.b[0], f.b[1], sv + 8 * kCellThreads, b_iso[i2], lo, hi, pb);
-        const int cs = edge_sum(f.s[0], f.s[1], sv + 16 * kCellThreads, s_iso[is], lo, hi, ps);
-        idx[3 * c] = (int16_t)is; idx[3 * c + 1] = (int16_t)i1; idx[3 * c + 2] = (int16_t)i2;
-        mask[c] = 1;
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {  // intersection.cu:203-213
-            const float xs = cs > 0 ? __fdiv_rn(ps[d], (float)cs) : ps[d];
-            const float xa = ca > 0 ? __fdiv_rn(pa[d], (float)ca) : pa[d];
-            const float xb = cb > 0 ? __fdiv_rn(pb[d], (float)cb) : pb[d];
-            pts[3 * c + d] = (float)((double)(xs + xa + xb) / 3.0);
-        }
-    }
-}
-
-
-// =====================================================================================================================
-// Fused path: ONE pass over the voxels.  (north star: "TMA-staged field tiles")
-//
-// The two-kernel form above reads the fields twice: `elect` streams all of them, `cell` gathers the winner voxels again
-// (3.8 M winners x 128 B at the reference's size) and evaluates 3 edge sums per CELL.  Here a tile of 256 consecutive
-// voxels is staged ONCE in shared memory (cp.async.bulk + mbarrier, double buffered: the next tile's 27 KB are in flight
-// while this one is processed) and serves both steps:
-//   phase A  one thread per voxel: min/max, index windows, atomicMin of its index into the cells it hits; hitting voxels
-//            are appended to a shared-memory list (warp-aggregated)
-//   publish  the tile's "phase A done" bit (release)
-//   wait     until every LOWER tile has published (acquire).  A voxel wins a cell iff no lower voxel hits it, so after
-//            this point `winner[c] == v` is final for this tile's voxels; higher tiles cannot take a cell away.
-//   phase B  the list is processed by all threads: winner check, then per voxel ONE edge mean per (field, isovalue of
-//            the window) -- 15.7 M instead of 24.6 M edge sums at the reference's size -- combined per won cell.
-// Tiles are handed out in ascending order by an atomic ticket, so the tiles a CTA waits for are always held by running
-// CTAs: no co-residency requirement, no grid barrier, no deadlock (the lowest unpublished tile never waits in phase A,
-// and a CTA's pending prefetched tile sits behind a tile whose own wait only involves lower, already published tiles).
-// DRAM traffic = the fields once + the outputs once; the winner array (4 B per cell) and the done bits live in L2.
-// =====================================================================================================================
-constexpr int kTileVox = 256;
-constexpr unsigned kNoWinner = 0xffffffffu;
-
-struct FusedSmem {
-    unsigned long long bar[2];
-    int nlist;
-    unsigned ticket[2];
-    int flag_ok;
-    int pad[2];
-    int4 list[kTileVox];                       // {local id, s0 | s1 << 16, a0 | a1 << 16, b0 | b1 << 16}
-    // per buffer: 3 fields x 256 voxels x 8 corners, then the centres
-    float4 f[2][3][kTileVox][2];
-    float ctr[2][kTileVox * 3];
-};
-
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ unsigned ld_relaxed_cg_u32(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ unsigned long long evict_first_policy() {
-    unsigned long long p;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-__device__ __forceinline__ void bulk_g2s_hint(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, unsigned long long pol) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(pol) : "memory");
-}
-__device__ __forceinline__ uint32_t fsmem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void fbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void fbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void fbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok = 0, spins = 0;
-    do {
-        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-        if (!ok && ++spins > (1u << 26)) { printf("inf3dp intersection: tile load timed out (block %d)\n", blockIdx.x); __trap(); }
-    } while (!ok);
-}
-
 // Mean edge-crossing point of one field at one isovalue (intersection.cu:135-160 + the division of :203-209): the 12
-// edges in the reference's order with compile-time corner ids (values stay in registers), inclusive test, unguarded IEEE
-// division, the same FMA contraction nvcc applies to `coord1 + t * (coord2 - coord1)`; on an axis the edge does not run
-// along, coord2 - coord1 is exactly 0, so the term is coord1 -- or NaN when t is not finite, which fmaf(t, 0, x) keeps.
+// edges in the reference's order with compile-time corner ids (the corner values stay in registers: no staging, no dynamic
+// indexing), inclusive test, unguarded IEEE division, the same FMA contraction nvcc applies to
+// `coord1 + t * (coord2 - coord1)`.  On an axis the edge does not run along, coord2 - coord1 is exactly 0, so the term is
+// coord1 -- or NaN when t is not finite (flat edge exactly at the isovalue), which fmaf(t, 0, x) preserves.
 __device__ __forceinline__ void edge_mean(const float4 q0, const float4 q1, float iso, const float* lo, const float* hi,
                                           float* out) {
     const float v[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
@@ -543,231 +388,56 @@ __device__ __forceinline__ void edge_mean(const float4 q0, const float4 q1, floa
     }
 }
 
-__device__ __forceinline__ void write_cell(long long c, int is, int i1, int i2, const float* ms, const float* ma, const float* mb,
-                                           uint8_t* __restrict__ mask, int16_t* __restrict__ idx, float* __restrict__ pts) {
-    mask[c] = 1;
-    idx[3 * c] = (int16_t)is; idx[3 * c + 1] = (int16_t)i1; idx[3 * c + 2] = (int16_t)i2;
-#pragma unroll
-    for (int d = 0; d < 3; ++d) pts[3 * c + d] = (float)((double)(ms[d] + ma[d] + mb[d]) / 3.0);   // intersection.cu:203-213
-}
+// pass 2, cell centric: one thread per cell.  A cell without a winner gets the "nothing here" outputs (mask 0,
+// indices -1, point 0: no separate initialisation pass); otherwise the cell's winner voxel is re-read (96 B of corner
+// fields + its centre) and the three edge sums are evaluated for exactly this cell's isovalues.  Uniform work per
+// thread, no index windows.  A block covers 8 consecutive slice isovalues x 32 consecutive lattice-2 isovalues of one
+// lattice-1 isovalue: every warp writes 32 consecutive cells (coalesced rows), and the 8 warps mostly re-read the SAME
+// winner voxels (a voxel typically spans 2-3 neighbouring slice isovalues), which the L1 serves.
+constexpr int kCellTileS = 8, kCellTile2 = 32;
 
 template <bool GRID>
-__global__ void __launch_bounds__(kTileVox, 3)
-isect_fused_kernel(const FieldSrc src, const float* __restrict__ s_iso, const float* __restrict__ a_iso,
-                   const float* __restrict__ b_iso, long long voxels, unsigned n_tiles, int Dx, int Ns, int N1, int N2,
-                   IsectWs w, int centers_aligned, uint8_t* __restrict__ mask, int16_t* __restrict__ idx,
-                   float* __restrict__ pts) {
-    extern __shared__ __align__(128) unsigned char fused_smem[];
-    FusedSmem& sm = *reinterpret_cast<FusedSmem*>(fused_smem);
-    const IsoTables tb = load_tables(w, fused_smem + sizeof(FusedSmem), Ns, N1, N2);
-    const int tid = threadIdx.x, lane = tid & 31;
-    unsigned* const winner = reinterpret_cast<unsigned*>(w.winner);
-    unsigned* const done = w.ctrl + 4;
-    const float vs = (float)(2.0 / (double)(float)Dx);  // intersection.cu:54
-    const unsigned long long pol = evict_first_policy();
-    if (tid == 0) {
-        fbar_init(fsmem_u32(&sm.bar[0]), 1);
-        fbar_init(fsmem_u32(&sm.bar[1]), 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        sm.ticket[0] = atomicAdd(&w.ctrl[0], 1u);
-        sm.nlist = 0;
-    }
-    __syncthreads();
-    unsigned parity[2] = {0u, 0u};
-    unsigned known = 0;              // every tile < known has published (this CTA has seen it)
-
-    // Stage tile t into buffer b.  Full tiles of the expanded layout: four bulk copies (3 x 8 KB + 3 KB) tracked by the
-    // buffer's mbarrier.  Ragged last tile, unaligned centres, grid mode: plain loads by the tile's threads.
-    auto tile_is_bulk = [&](unsigned t) -> bool {
-        return !GRID && centers_aligned && (long long)(t + 1) * kTileVox <= voxels;
-    };
-    auto stage = [&](unsigned t, int b) {
-        const long long v0 = (long long)t * kTileVox;
-        if (tile_is_bulk(t)) {
-            if (tid == 0) {
-                const uint32_t bar = fsmem_u32(&sm.bar[b]);
-                fbar_expect_tx(bar, 3u * kTileVox * 32u + kTileVox * 12u);
-                bulk_g2s_hint(fsmem_u32(&sm.f[b][0][0][0]), src.sf + 8 * v0, kTileVox * 32u, bar, pol);
-                bulk_g2s_hint(fsmem_u32(&sm.f[b][1][0][0]), src.af + 8 * v0, kTileVox * 32u, bar, pol);
-                bulk_g2s_hint(fsmem_u32(&sm.f[b][2][0][0]), src.bf + 8 * v0, kTileVox * 32u, bar, pol);
-                bulk_g2s_hint(fsmem_u32(&sm.ctr[b][0]), src.centers + 3 * v0, kTileVox * 12u, bar, pol);
-            }
-        } else {
-            const long long v = v0 + tid;
-            if (v < voxels) {
-                VoxelFields f;
-                load_voxel<GRID, true>(src, v, f);
-                float c[3];
-                load_center<GRID>(src, v, c);
-                sm.f[b][0][tid][0] = f.s[0]; sm.f[b][0][tid][1] = f.s[1];
-                sm.f[b][1][tid][0] = f.a[0]; sm.f[b][1][tid][1] = f.a[1];
-                sm.f[b][2][tid][0] = f.b[0]; sm.f[b][2][tid][1] = f.b[1];
-                sm.ctr[b][3 * tid] = c[0]; sm.ctr[b][3 * tid + 1] = c[1]; sm.ctr[b][3 * tid + 2] = c[2];
-            }
-        }
-    };
-
-    unsigned t_cur = sm.ticket[0];
-    int b = 0;
-    if (t_cur < n_tiles) stage(t_cur, 0);
-    while (t_cur < n_tiles) {
-        if (tid == 0) sm.ticket[b ^ 1] = atomicAdd(&w.ctrl[0], 1u);
-        __syncthreads();                       // ticket visible; phase B of the previous tile is over: buffer b^1 and the list are free
-        const unsigned t_next = sm.ticket[b ^ 1];
-        if (t_next < n_tiles) stage(t_next, b ^ 1);
-        if (tile_is_bulk(t_cur)) { fbar_wait(fsmem_u32(&sm.bar[b]), parity[b]); parity[b] ^= 1u; }
-        else __syncthreads();                  // plain stores of stage(t_cur) (issued one iteration ago, or in the prologue)
-
-        // ---------------- phase A: windows + election ----------------
-        const long long v = (long long)t_cur * kTileVox + tid;
-        bool hit = false;
-        Windows r{};
-        if (v < voxels) {
-            VoxelFields f;
-            f.s[0] = sm.f[b][0][tid][0]; f.s[1] = sm.f[b][0][tid][1];
-            f.a[0] = sm.f[b][1][tid][0]; f.a[1] = sm.f[b][1][tid][1];
-            f.b[0] = sm.f[b][2][tid][0]; f.b[1] = sm.f[b][2][tid][1];
-            r = voxel_windows(f, tb);
-            hit = r.any;
-            if (hit) {
-                for (int ja = r.a0; ja < r.a1; ++ja) {
-                    const int i1 = tb.perm[1][ja];
-                    for (int jb = r.b0; jb < r.b1; ++jb) {
-                        const int i2 = tb.perm[2][jb];
-                        for (int js = r.s0; js < r.s1; ++js) {
-                            const long long c = ((long long)tb.perm[0][js] * N1 + i1) * N2 + i2;
-                            // tiles run in roughly ascending order: most of the time the cell already holds a smaller
-                            // index, and a plain L2 load is much cheaper than an L2 atomic
-                            if (ld_relaxed_cg_u32(&winner[c]) > (unsigned)v) atomicMin(&winner[c], (unsigned)v);
-                        }
-                    }
-                }
-            }
-        }
-        {
-            const unsigned bal = __ballot_sync(0xffffffffu, hit);
-            int base = 0;
-            if (lane == 0 && bal) base = atomicAdd(&sm.nlist, __popc(bal));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (hit) sm.list[base + __popc(bal & ((1u << lane) - 1u))] =
-                make_int4(tid, r.s0 | (r.s1 << 16), r.a0 | (r.a1 << 16), r.b0 | (r.b1 << 16));
-        }
-        __threadfence();                       // this thread's atomics are ordered before the publication below
-        __syncthreads();
-        const int nlist = sm.nlist;
-        if (tid == 0) {
-            asm volatile("red.release.gpu.global.or.b32 [%0], %1;" ::"l"(done + (t_cur >> 5)), "r"(1u << (t_cur & 31)) : "memory");
-        }
-
-        // ---------------- wait: every lower tile has published ----------------
-        if (nlist > 0 && known < t_cur) {
-            if (tid < 32) {
-                const unsigned g = ld_acquire_u32(&w.ctrl[1]);
-                if (g > known) known = g;
-                unsigned spins = 0;
-                while (known < t_cur) {
-                    // words [known / 32, t_cur / 32], 32 per round; lane i checks word (known / 32) + i
-                    const unsigned w0 = known >> 5, wl = (t_cur - 1) >> 5;
-                    const unsigned wi = w0 + lane;
-                    unsigned need = 0, have = 0;
-                    if (wi <= wl) {
-                        need = 0xffffffffu;
-                        if (wi == w0) need &= 0xffffffffu << (known & 31);
-                        if (wi == wl && (t_cur & 31)) need &= (1u << (t_cur & 31)) - 1u;
-                        have = ld_acquire_u32(done + wi);
-                    }
-                    const unsigned bad = __ballot_sync(0xffffffffu, (have & need) != need);
-                    if (bad == 0) {
-                        known = min(t_cur, (w0 + 32u) << 5);
-                    } else {
-                        const int fl = __ffs(bad) - 1;                        // first lane with a missing bit
-                        const unsigned miss = __shfl_sync(0xffffffffu, ~have & need, fl);
-                        known = ((w0 + fl) << 5) + (__ffs(miss) - 1);
-                        if (++spins > 64u) __nanosleep(64);
-                        if (spins > (1u << 24)) { printf("inf3dp intersection: prefix wait timed out (block %d tile %u known %u)\n", blockIdx.x, t_cur, known); __trap(); }
-                    }
-                }
-                if (lane == 0) { atomicMax(&w.ctrl[1], known); sm.flag_ok = (int)known; }
-            }
-            __syncthreads();
-            known = (unsigned)sm.flag_ok;
-        }
-
-        // ---------------- phase B: evaluate the won cells ----------------
-        for (int e = tid; e < nlist; e += kTileVox) {
-            const int4 ent = sm.list[e];
-            const int id = ent.x;
-            const unsigned vv = (unsigned)((long long)t_cur * kTileVox + id);
-            const int s0 = ent.y & 0xffff, s1 = ent.y >> 16, a0 = ent.z & 0xffff, a1 = ent.z >> 16, b0 = ent.w & 0xffff, b1 = ent.w >> 16;
-            float lo[3], hi[3];
-#pragma unroll
-            for (int d = 0; d < 3; ++d) { const float cc = sm.ctr[b][3 * id + d]; lo[d] = fmaf(vs, -0.5f, cc); hi[d] = fmaf(vs, 0.5f, cc); }
-            if (a1 - a0 == 1 && b1 - b0 == 1 && s1 - s0 <= 8) {
-                // the usual shape: one lattice isovalue each, a few slice isovalues.  All winner loads first, then the
-                // edge means in the same order on every lane (the warp stays converged through the three call sites).
-                const int i1 = tb.perm[1][a0], i2 = tb.perm[2][b0];
-                unsigned won = 0;
-                unsigned wv[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u)
-                    wv[u] = (s0 + u < s1) ? ld_relaxed_cg_u32(&winner[((long long)tb.perm[0][s0 + u] * N1 + i1) * N2 + i2]) : kNoWinner;
-#pragma unroll
-                for (int u = 0; u < 8; ++u) won |= (wv[u] == vv) ? (1u << u) : 0u;
-                if (won) {
-                    float ma[3], mb[3];
-                    edge_mean(sm.f[b][1][id][0], sm.f[b][1][id][1], a_iso[i1], lo, hi, ma);
-                    edge_mean(sm.f[b][2][id][0], sm.f[b][2][id][1], b_iso[i2], lo, hi, mb);
-                    const float4 q0 = sm.f[b][0][id][0], q1 = sm.f[b][0][id][1];
-                    while (won) {
-                        const int u = __ffs(won) - 1;
-                        won &= won - 1;
-                        const int is = tb.perm[0][s0 + u];
-                        float ms[3];
-                        edge_mean(q0, q1, s_iso[is], lo, hi, ms);
-                        write_cell(((long long)is * N1 + i1) * N2 + i2, is, i1, i2, ms, ma, mb, mask, idx, pts);
-                    }
-                }
-            } else {
-                for (int ja = a0; ja < a1; ++ja) {
-                    const int i1 = tb.perm[1][ja];
-                    bool have_a = false;
-                    float ma[3];
-                    for (int jb = b0; jb < b1; ++jb) {
-                        const int i2 = tb.perm[2][jb];
-                        bool have_b = false;
-                        float mb[3];
-                        for (int js = s0; js < s1; ++js) {
-                            const int is = tb.perm[0][js];
-                            const long long c = ((long long)is * N1 + i1) * N2 + i2;
-                            if (ld_relaxed_cg_u32(&winner[c]) != vv) continue;
-                            if (!have_a) { edge_mean(sm.f[b][1][id][0], sm.f[b][1][id][1], a_iso[i1], lo, hi, ma); have_a = true; }
-                            if (!have_b) { edge_mean(sm.f[b][2][id][0], sm.f[b][2][id][1], b_iso[i2], lo, hi, mb); have_b = true; }
-                            float ms[3];
-                            edge_mean(sm.f[b][0][id][0], sm.f[b][0][id][1], s_iso[is], lo, hi, ms);
-                            write_cell(c, is, i1, i2, ms, ma, mb, mask, idx, pts);
-                        }
-                    }
-                }
-            }
-        }
-        if (tid == 0) sm.nlist = 0;            // ordered before the next tile's appends by the barrier at the loop head
-        b ^= 1;
-        t_cur = t_next;
-    }
-}
-
-// Cells no voxel hit get the reference's initial values (intersection.cu:246-248: mask 0, indices -1, point 0).
 __global__ void __launch_bounds__(256)
-isect_defaults_kernel(long long cells, const unsigned* __restrict__ winner, uint8_t* __restrict__ mask,
-                      int16_t* __restrict__ idx, float* __restrict__ pts) {
-    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < cells; c += (long long)gridDim.x * blockDim.x) {
-        if (__ldcs(winner + c) == kNoWinner) {
+isect_cell_kernel(const FieldSrc src, const float* __restrict__ s_iso, const float* __restrict__ a_iso,
+                  const float* __restrict__ b_iso, int Dx, int Ns, int N1, int N2, long long tiles, IsectWs w,
+                  uint8_t* __restrict__ mask, int16_t* __restrict__ idx, float* __restrict__ pts) {
+    const float vs = (float)(2.0 / (double)(float)Dx);  // intersection.cu:54
+    const int tiles2 = (N2 + kCellTile2 - 1) / kCellTile2;
+    const int r = threadIdx.x >> 5, q = threadIdx.x & 31;
+    for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const int t2 = (int)(t % tiles2);
+        const long long u = t / tiles2;
+        const int i1 = (int)(u % N1);
+        const int ts = (int)(u / N1);
+        const int is = ts * kCellTileS + r, i2 = t2 * kCellTile2 + q;
+        if (is >= Ns || i2 >= N2) continue;
+        const long long c = ((long long)is * N1 + i1) * N2 + i2;
+        const int v = __ldcs(&w.winner[c]);
+        if (v == 0x7fffffff) {
             mask[c] = 0;
             idx[3 * c] = -1; idx[3 * c + 1] = -1; idx[3 * c + 2] = -1;
             pts[3 * c] = 0.f; pts[3 * c + 1] = 0.f; pts[3 * c + 2] = 0.f;
+            continue;
         }
+        VoxelFields f;
+        load_voxel<GRID, false>(src, v, f);
+        float ctr[3];
+        load_center<GRID>(src, v, ctr);
+        // corner coordinates: centre + voxel_size * (-0.5 | +0.5), the two values per axis shared by all three fields
+        float lo[3], hi[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) { lo[d] = fmaf(vs, -0.5f, ctr[d]); hi[d] = fmaf(vs, 0.5f, ctr[d]); }
+        float pa[3], pb[3], ps[3];
+        edge_mean(f.a[0], f.a[1], a_iso[i1], lo, hi, pa);
+        edge_mean(f.b[0], f.b[1], b_iso[i2], lo, hi, pb);
+        edge_mean(f.s[0], f.s[1], s_iso[is], lo, hi, ps);
+        idx[3 * c] = (int16_t)is; idx[3 * c + 1] = (int16_t)i1; idx[3 * c + 2] = (int16_t)i2;
+        mask[c] = 1;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) pts[3 * c + d] = (float)((double)(ps[d] + pa[d] + pb[d]) / 3.0);  // intersection.cu:203-213
     }
 }
+
 
 template <bool GRID>
 int isect_run(const FieldSrc& src, const float* s_iso, const float* a_iso, const float* b_iso, int Dx, int Dy, int Dz,
@@ -790,31 +460,8 @@ int isect_run(const FieldSrc& src, const float* s_iso, const float* a_iso, const
         return INF3DP_EWORKSPACE;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    isect_prep_kernel<<<1, 1024, 0, st>>>(s_iso, a_iso, b_iso, Ns, N1, N2, w);
+    isect_prep_kernel<<<3, 1024, 8192 * sizeof(float), st>>>(s_iso, a_iso, b_iso, Ns, N1, N2, w);
     INF3DP_LAUNCH_CHECK("isect_prep_kernel");
-    static const bool legacy = getenv("INF3DP_ISECT_LEGACY") != nullptr;   // developer switch: the two-kernel form, for A/B timing
-    if (!legacy) {
-        INF3DP_CUDA(cudaMemsetAsync(w.winner, 0xff, w.winner_bytes, st));
-        INF3DP_CUDA(cudaMemsetAsync(w.ctrl, 0, w.ctrl_bytes, st));
-        if (voxels > 0) {
-            const unsigned n_tiles = (unsigned)((voxels + kTileVox - 1) / kTileVox);
-            const size_t tab_smem = (Ns + N1 + N2) <= kMaxTableEntries ? (size_t)(Ns + N1 + N2) * 8 : 0;
-            const size_t smem = sizeof(FusedSmem) + tab_smem;
-            INF3DP_CUDA(cudaFuncSetAttribute(isect_fused_kernel<GRID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            int per_sm = 0;
-            INF3DP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, isect_fused_kernel<GRID>, kTileVox, smem));
-            if (per_sm < 1) per_sm = 1;
-            const unsigned grid = (unsigned)std::min<long long>(n_tiles, (long long)num_sms() * per_sm);
-            const int centers_aligned = GRID ? 0 : ((reinterpret_cast<uintptr_t>(src.centers) & 15) == 0);
-            isect_fused_kernel<GRID><<<grid, kTileVox, smem, st>>>(src, s_iso, a_iso, b_iso, voxels, n_tiles, Dx, Ns, N1, N2, w,
-                                                                   centers_aligned, mask, idx, pts);
-            INF3DP_LAUNCH_CHECK("isect_fused_kernel");
-        }
-        const long long blocks = std::min<long long>((cells + 255) / 256, (long long)num_sms() * 16);
-        isect_defaults_kernel<<<(unsigned)blocks, 256, 0, st>>>(cells, reinterpret_cast<const unsigned*>(w.winner), mask, idx, pts);
-        INF3DP_LAUNCH_CHECK("isect_defaults_kernel");
-        return INF3DP_OK;
-    }
     const long long quads = (cells + 3) / 4;
     isect_init_kernel<<<(unsigned)((quads + 255) / 256), 256, 0, st>>>(cells, w.winner);
     INF3DP_LAUNCH_CHECK("isect_init_kernel");

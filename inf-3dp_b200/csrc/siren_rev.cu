@@ -96,11 +96,20 @@ struct RevCfg {
 // KIND 2: the level classifier of the collision query (exp_scripts/train_levels.py:35-51, utils.py:269-303): ReLU MLP
 //         4 -> 256 -> 256 -> C (C <= 16), value only.  One GEMM per tile of 128 points; layer 0 (4 -> 256) and the linear
 //         output layer (256 -> C, folded into the hidden layer's epilogue) are FP32 CUDA-core work.
+// Destinations of the packed (value, grad) rows when the query is fused with the multi-GPU all-gather (KIND 0 only):
+// either one NVLink multicast address (multimem.st, replicated by the switch) or up to 8 peer-mapped buffers.
+constexpr int kMaxRowPeers = 8;
+struct RowPeers {
+    float4* dst[kMaxRowPeers];
+    float4* mc;
+    int n;
+};
+
 template <int CTAS, int KIND>
 __global__ void __launch_bounds__(kThreads, 1)
 siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __restrict__ x, int64_t n,
                  float* __restrict__ y, float* __restrict__ J, float* __restrict__ Hout, float4* __restrict__ stash,
-                 unsigned long long* __restrict__ dbg) {
+                 unsigned long long* __restrict__ dbg, const RowPeers peers) {
     using C = RevCfg<CTAS>;
     constexpr int kGemms = KIND == 0 ? 6 : (KIND == 1 ? 3 : 1);
     constexpr int kTilePts = KIND == 1 ? 12 : 128;
@@ -650,7 +659,19 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
                     r4[o] = ((s_part[(0 * 4 + o) * 128 + row] + s_part[(1 * 4 + o) * 128 + row]) +
                              s_part[(2 * 4 + o) * 128 + row]) + s_part[(3 * 4 + o) * 128 + row];
                 const float inv_g = s_misc[4];
-                if (Hout != nullptr) {   // packed rows (value, d/dx, d/dy, d/dz): one 16-byte store per point
+                if (peers.mc != nullptr) {
+                    // fused all-gather, NVLink multicast: ONE store per point, the NVSwitch replicates the row into the
+                    // gathered buffer of every rank (this one included)
+                    float4* q = peers.mc + pt;
+                    asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};"
+                                 ::"l"(q), "f"(r4[0] + s_misc[3]), "f"(r4[1] * inv_g), "f"(r4[2] * inv_g), "f"(r4[3] * inv_g) : "memory");
+                } else if (peers.n > 0) {
+                    // fused all-gather, peer-to-peer: the row goes straight into every rank's gathered buffer over NVLink
+                    const float4 rowv = make_float4(r4[0] + s_misc[3], r4[1] * inv_g, r4[2] * inv_g, r4[3] * inv_g);
+#pragma unroll
+                    for (int g = 0; g < kMaxRowPeers; ++g)
+                        if (g < peers.n) peers.dst[g][pt] = rowv;
+                } else if (Hout != nullptr) {   // packed rows (value, d/dx, d/dy, d/dz): one 16-byte store per point
                     reinterpret_cast<float4*>(Hout)[pt] = make_float4(r4[0] + s_misc[3], r4[1] * inv_g, r4[2] * inv_g, r4[3] * inv_g);
                 } else {
                     y[pt] = r4[0] + s_misc[3];
@@ -766,7 +787,7 @@ __global__ void mlp_pack_out_kernel(const float* __restrict__ W2, const float* _
 
 template <int CTAS, int KIND>
 int launch_rev(const void* packed, const SirenHeader& h, const float* x, int64_t n, float* y, float* J, float* H, void* ws,
-               cudaStream_t stream) {
+               cudaStream_t stream, const RowPeers peers = RowPeers{}) {
     using C = RevCfg<CTAS>;
     auto kern = siren_rev_kernel<CTAS, KIND>;
     const int smem = (int)(KIND == 2 ? C::kSmemTotalMlp : C::kSmemTotal) + 1024;
@@ -794,7 +815,7 @@ int launch_rev(const void* packed, const SirenHeader& h, const float* x, int64_t
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    INF3DP_CUDA(cudaLaunchKernelEx(&cfg, kern, (const char*)packed, h, x, n, y, J, H, (float4*)ws, dbg));
+    INF3DP_CUDA(cudaLaunchKernelEx(&cfg, kern, (const char*)packed, h, x, n, y, J, H, (float4*)ws, dbg, peers));
     INF3DP_LAUNCH_CHECK("siren_rev_kernel");
     if (debug) {
         unsigned long long hbuf[64];
@@ -882,6 +903,32 @@ int siren_rev_launch_rows(const void* packed, const SirenHeader& h, const float*
                      siren_rev_workspace_bytes(), ws_bytes);
     INF3DP_CHECK_ARG((reinterpret_cast<uintptr_t>(rows) & 15) == 0, "siren_rev: rows must be 16-byte aligned");
     return launch_rev<2, 0>(packed, h, x, n, nullptr, nullptr, rows, ws, stream);
+}
+
+// Same rows, stored by the kernel's epilogue directly into the gathered buffers of the ranks of a multi-GPU job: the
+// query fused with its all-gather (the one collective of the sharded path).
+int siren_rev_launch_rows_peers(const void* packed, const SirenHeader& h, const float* x, int64_t n, float* const* peer_rows,
+                                int n_peers, float* multicast_rows, void* ws, size_t ws_bytes, cudaStream_t stream) {
+    INF3DP_CHECK_ARG(h.rev_ok && h.off_rev != 0, "siren_rev: packed weights carry no reverse-mode section");
+    INF3DP_CHECK_ARG(ws != nullptr && ws_bytes >= siren_rev_workspace_bytes(),
+                     "siren_rev: workspace of %zu bytes needed (inf3dp_siren_jet_workspace_bytes), got %zu",
+                     siren_rev_workspace_bytes(), ws_bytes);
+    INF3DP_CHECK_ARG(multicast_rows != nullptr || (n_peers >= 1 && n_peers <= kMaxRowPeers && peer_rows != nullptr),
+                     "siren_rev: need a multicast address or 1..%d peer row buffers", kMaxRowPeers);
+    RowPeers peers{};
+    peers.mc = reinterpret_cast<float4*>(multicast_rows);
+    INF3DP_CHECK_ARG((reinterpret_cast<uintptr_t>(multicast_rows) & 15) == 0, "siren_rev: multicast rows must be 16-byte aligned");
+    if (multicast_rows == nullptr) {
+        peers.n = n_peers;
+        for (int g = 0; g < n_peers; ++g) {
+            INF3DP_CHECK_ARG(peer_rows[g] != nullptr && (reinterpret_cast<uintptr_t>(peer_rows[g]) & 15) == 0,
+                             "siren_rev: peer row buffer %d is null or not 16-byte aligned", g);
+            peers.dst[g] = reinterpret_cast<float4*>(peer_rows[g]);
+        }
+    }
+    // a non-null Hout selects the rows epilogue; it is never dereferenced when peers are given
+    float* tag = multicast_rows != nullptr ? multicast_rows : peer_rows[0];
+    return launch_rev<2, 0>(packed, h, x, n, nullptr, nullptr, tag, ws, stream, peers);
 }
 
 // Value + gradient + Hessian (order 2) of single-output networks: forward-mode second-order jet on the CTA-pair engine.

@@ -33,6 +33,7 @@ SIGNATURES = {
     "inf3dp_unit_normals": (_i, [_vp, _i64, _f, _vp, _vp]),
     "inf3dp_unit_normals_rows": (_i, [_vp, _i64, _f, _vp, _vp]),
     "inf3dp_siren_value_grad_rows": (_i, [_vp, _vp, _i64, _vp, _vp, _sz, _vp]),
+    "inf3dp_siren_value_grad_rows_peers": (_i, [_vp, _vp, _i64, _vp, _i, _vp, _vp, _sz, _vp]),
     "inf3dp_extract_isocontours_workspace_bytes": (_sz, [_i, _i, _i]),
     "inf3dp_extract_isocontours_workspace_bytes_segments": (_sz, [_i, _i, _i, _i64]),
     "inf3dp_extract_isocontours": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),

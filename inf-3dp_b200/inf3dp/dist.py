@@ -129,6 +129,113 @@ class PipelinedAllGather:
         return self.gathered[:, r].reshape(self.chunks * self.m, self.width)[:self.n_local]
 
 
+class FusedRowGather:
+    """The all-gather of the sharded SIREN query FUSED INTO THE QUERY KERNEL.
+
+    Every rank owns `n_local` points; the result is `self.gathered` [world, n_local, 4] = the (value, grad) rows of every
+    rank, identical on all ranks.  The buffer is symmetric memory (torch.distributed._symmetric_memory: every rank's copy
+    is mapped into every process).  `query()` launches the reverse-mode engine with the peer mappings: its epilogue stores
+    each finished row into ALL ranks' buffers over NVLink -- through ONE multimem.st to the NVLink multicast address when
+    the fabric supports it (the NVSwitch replicates), otherwise through one store per peer.  There is no communication
+    kernel: no SM is reserved, nothing runs after the last tile except a cross-rank barrier.
+
+        fg = FusedRowGather(n_local, device)
+        fg.begin()                       # barrier: every rank is done reading the previous result
+        fg.query(net, coords_local)      # one launch (or several with row_offset) over the local shard
+        fg.finish()                      # barrier: every rank's rows have landed everywhere
+        fg.gathered[r]                   # rows of rank r
+
+    mode: "multicast" | "p2p" (what is in use), chosen by `prefer`."""
+
+    def __init__(self, n_local, device, group=None, prefer="multicast"):
+        import torch.distributed._symmetric_memory as symm
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        if self.world > 8:
+            raise RuntimeError("FusedRowGather: at most 8 ranks (one NVSwitch domain)")
+        self.n_local = int(n_local)
+        self.device = torch.device(device)
+        self.gathered = symm.empty((self.world, self.n_local, 4), dtype=torch.float32, device=self.device)
+        self.hdl = symm.rendezvous(self.gathered, self.group)
+        self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        mc = 0
+        if prefer == "multicast":
+            try:
+                if self.hdl.has_multicast_support:
+                    mc = int(self.hdl.multicast_ptr)
+            except Exception:
+                mc = 0
+        self.mc = mc
+        self.mode = "multicast" if mc else "p2p"
+
+    def begin(self):
+        self.hdl.barrier(channel=0)
+
+    def query(self, net, coords, row_offset=0):
+        off = (self.rank * self.n_local + int(row_offset)) * 16
+        net.query_rows_peers(coords, [p + off for p in self.ptrs], (self.mc + off) if self.mc else 0)
+
+    def local_rows(self):
+        return self.gathered[self.rank]
+
+    def finish(self):
+        self.hdl.barrier(channel=1)
+
+    def rows_of_rank(self, r):
+        return self.gathered[r]
+
+
+class ShardedHostPipeline:
+    """The sharded query END TO END for host-resident coordinates: every rank streams ITS shard of the coordinates from
+    pinned host memory (H2D of chunk i+1 under the kernel of chunk i), the kernel's epilogue all-gathers the rows into every
+    rank's HBM (FusedRowGather), and every rank copies the rows of ONE shard -- `source_rank`, by default its own -- back to
+    its host buffer (D2H of chunk i-1 under the kernel of chunk i).  With source_rank != rank the host result of a rank has
+    travelled H2D on another GPU -> tensor cores there -> NVLink -> D2H here: the collective is on the timed path.
+
+    A cross-rank barrier follows each chunk's launch (the rows of chunk i are complete on every rank before anybody copies
+    them out) and precedes the first one (every rank has finished reading the previous run's rows)."""
+
+    def __init__(self, net, n_local, chunk=1 << 23, device=None, group=None, prefer="multicast"):
+        self.net = net
+        self.n_local, self.chunk = int(n_local), int(chunk)
+        self.device = torch.device(device if device is not None else torch.cuda.current_device())
+        self.fg = FusedRowGather(n_local, self.device, group, prefer)
+        dev = self.device
+        self.s_in, self.s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        self.d_x = [torch.empty((self.chunk, 3), dtype=torch.float32, device=dev) for _ in range(2)]
+        self.ev_in = [torch.cuda.Event() for _ in range(2)]
+        self.ev_k = [torch.cuda.Event() for _ in range(2)]
+
+    @torch.no_grad()
+    def run(self, coords_host, out_host, source_rank=None):
+        src = self.fg.rank if source_rank is None else int(source_rank)
+        n = coords_host.shape[0]
+        if n != self.n_local:
+            raise RuntimeError("ShardedHostPipeline.run: coords_host must hold this rank's n_local points")
+        cur = torch.cuda.current_stream(self.device)
+        self.fg.begin()
+        nchunks = (n + self.chunk - 1) // self.chunk
+        for i in range(nchunks):
+            b = i & 1
+            lo, hi = i * self.chunk, min(n, (i + 1) * self.chunk)
+            m = hi - lo
+            with torch.cuda.stream(self.s_in):
+                if i >= 2:
+                    self.s_in.wait_event(self.ev_k[b])
+                self.d_x[b][:m].copy_(coords_host[lo:hi], non_blocking=True)
+                self.ev_in[b].record(self.s_in)
+            cur.wait_event(self.ev_in[b])
+            self.fg.query(self.net, self.d_x[b][:m], row_offset=lo)
+            self.fg.finish()                       # every rank's rows of chunk i have landed everywhere
+            self.ev_k[b].record(cur)
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(self.ev_k[b])
+                out_host[lo:hi].copy_(self.fg.gathered[src, lo:hi], non_blocking=True)
+        self.s_out.synchronize()
+        return out_host
+
+
 def reserve_sms(n):
     """Keep `n` SMs free of the persistent SIREN engines (0 = use all), so that NCCL kernels launched on another stream can
     run next to them (include/inf3dp.h: inf3dp_siren_set_sm_limit)."""

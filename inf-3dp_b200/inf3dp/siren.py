@@ -129,6 +129,24 @@ def value_grad_rows(blob, x, out=None):
     return out.view(-1, 4)[:n] if out.dim() != 2 or out.shape[0] != n else out
 
 
+def value_grad_rows_peers(blob, x, peer_ptrs, multicast_ptr=0):
+    """x [n,3] (CUDA, f32): the (value, grad) rows are stored by the kernel's epilogue directly at the given peer-mapped
+    device addresses (ints; one per rank of the job, each = destination of row 0 of this call), or through ONE NVLink
+    multicast address -- include/inf3dp.h: inf3dp_siren_value_grad_rows_peers.  Nothing is returned: the rows live in the
+    callers' gathered buffers (see inf3dp.dist.FusedRowGather)."""
+    if not x.is_cuda:
+        raise RuntimeError("inf3dp: coords must be a CUDA tensor (no CPU fallback)")
+    x = x.detach().to(torch.float32).contiguous()
+    n = x.shape[0]
+    dev = x.device
+    ws = _jet_workspace(dev)
+    arr = (ctypes.c_void_p * max(1, len(peer_ptrs)))(*[int(p) for p in peer_ptrs])
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().inf3dp_siren_value_grad_rows_peers(_lib.ptr(blob), _lib.ptr(x), n, arr, len(peer_ptrs),
+                                                                 ctypes.c_void_p(int(multicast_ptr)) if multicast_ptr else None,
+                                                                 _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)))
+
+
 class _SirenJacobian(torch.autograd.Function):
     """J(x) as a differentiable node: its backward contracts with the Hessian of an order-2 launch."""
 
@@ -234,6 +252,14 @@ class FusedSirenMixin:
         ws, bs = self._weights()
         blob = self._packed.get(ws, bs)
         return value_grad_rows(blob, coords.reshape(-1, coords.shape[-1]), out)
+
+
+    @torch.no_grad()
+    def query_rows_peers(self, coords, peer_ptrs, multicast_ptr=0):
+        """query_rows with the rows stored straight into peer-mapped buffers / an NVLink multicast address."""
+        ws, bs = self._weights()
+        blob = self._packed.get(ws, bs)
+        value_grad_rows_peers(blob, coords.reshape(-1, coords.shape[-1]), peer_ptrs, multicast_ptr)
 
 
 class SingleBVPNet(FusedSirenMixin, nn.Module):
