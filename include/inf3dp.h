@@ -218,6 +218,40 @@ int inf3dp_marching_cubes_emit(const float* volume, int Gx, int Gy, int Gz, floa
                                float* normals, float* values, int64_t n_verts, int64_t n_faces, void* workspace,
                                size_t workspace_bytes, inf3dp_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * TV-SDF collision query: the fused predicate / compaction stages between the field sweeps.
+ * Replaces the mask / nonzero / gather / where glue of level_collision.CollTVSDF.forward (level_collision.py:73-237) and
+ * the posing of utils.transform_nozzle_pcd_with_quaternion (utils.py:612-621); the sweeps themselves are
+ * inf3dp_siren_jet_ws / inf3dp_siren_value_grad_rows launches on the compact lists these stages write.
+ * Point ids: p = waypoint * M + nozzle point (< 2^30 per call).  counters: int32[8] on the device
+ * ([0] cube list, [1] inside list, [2] recheck list, [3] points whose result carries the SDF gradient); inf3dp_coll_pose
+ * zeroes them, the caller reads a count back before it launches the next sweep.
+ * Outputs ("out surface", either or both): per point depth_p [P] / mask_p [P] / grads_p [P,3] (the CollTVSDF surface; the
+ * caller pre-zeroes them) and / or per waypoint depth_w [Nw] (max depth as IEEE bits, pre-zeroed) / hit_w [Nw].
+ * ------------------------------------------------------------------------------------------------------- */
+int inf3dp_coll_pose(const float* waypts, const float* quats /* [Nw,4] or NULL */, const float* nozzle_or_posed_cloud,
+                     int64_t Nw, int M, float base_th, float* cube_x, int32_t* cube_id, int32_t* counters, float* depth_p,
+                     uint8_t* mask_p, float* grads_p, uint32_t* depth_w, uint8_t* hit_w, inf3dp_stream_t stream);
+int inf3dp_coll_inside(const float* sdf, int64_t n, const float* cube_x, const int32_t* cube_id, float* in_x, int32_t* in_id,
+                       float* in_sdf, int32_t* counters, int M, float* depth_p, uint8_t* mask_p, float* grads_p,
+                       uint32_t* depth_w, uint8_t* hit_w, inf3dp_stream_t stream);
+int inf3dp_coll_pack4(const float* x3, const float* values, int value_stride, int64_t n, float* x4, inf3dp_stream_t stream);
+int inf3dp_coll_predicate(const float* slice_rows, const float* logits, int C, int64_t n, const float* in_x,
+                          const int32_t* in_id, const float* in_sdf, const int32_t* levels_w, const float* maxslices, int M,
+                          float* re_x, int32_t* re_src, float* re_dist, int32_t* grad_src, int want_grads, int32_t* counters,
+                          float* depth_p, uint8_t* mask_p, float* grads_p, uint32_t* depth_w, uint8_t* hit_w,
+                          inf3dp_stream_t stream);
+int inf3dp_coll_push(const float* slice_rows_at_push1, int64_t n, const float* re_x, const float* re_dist, float* push_x,
+                     inf3dp_stream_t stream);
+int inf3dp_coll_alter(const float* slice_at_push, const float* logits_at_push, int C, int64_t n, const int32_t* re_src,
+                      const float* re_dist, const float* slice_rows, const int32_t* in_id, const float* in_sdf,
+                      const int32_t* levels_w, const float* maxslices, int M, int32_t* grad_src, int want_grads,
+                      int32_t* counters, float* depth_p, uint8_t* mask_p, float* grads_p, uint32_t* depth_w, uint8_t* hit_w,
+                      inf3dp_stream_t stream);
+int inf3dp_coll_gather_x(const int32_t* grad_src, int64_t n, const float* in_x, float* gx, inf3dp_stream_t stream);
+int inf3dp_coll_scatter_grads(const float* sdf_rows, int64_t n, const int32_t* grad_src, const int32_t* in_id, float* grads_p,
+                              inf3dp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,7 +14,7 @@ from .projection import batch_isosurface_projection, iter_project_contours_batch
 from .volume import (grid_queries, grid_field, get_grid_fields, marching_cubes, sdf_to_mesh, gen_iso_layers,
                      get_fields_intersection_from_grids)
 from .collision import (CollTVSDF, collision_evaluation, tvsdf_collision_forward, quat_collision_sweep,
-                        transform_nozzle_pcd_with_quaternion)
+                        quat_collision_sweep_unfused, transform_nozzle_pcd_with_quaternion)
 
 
 def patch_reference(force=False):
@@ -43,7 +43,7 @@ __all__ = [
     "gradient", "hessian", "hessian3d", "jacobian",
     "divergence", "laplace", "principal_curvatures", "min_max_curvs_and_vectors", "unit_normals", "unit_normals_rows", "field_querying",
     "field_query_with_grads", "HostPipeline", "patch_reference", "batch_isosurface_projection",
-    "iter_project_contours_batch", "CollTVSDF", "collision_evaluation", "tvsdf_collision_forward", "quat_collision_sweep",
+    "iter_project_contours_batch", "CollTVSDF", "collision_evaluation", "tvsdf_collision_forward", "quat_collision_sweep", "quat_collision_sweep_unfused",
     "transform_nozzle_pcd_with_quaternion", "grid_queries", "grid_field", "get_grid_fields", "marching_cubes",
     "sdf_to_mesh", "gen_iso_layers", "get_fields_intersection_from_grids",
 ]

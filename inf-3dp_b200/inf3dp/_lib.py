@@ -44,6 +44,14 @@ SIGNATURES = {
     "inf3dp_fields_intersection_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "inf3dp_fields_intersection": (_i, [_vp] * 7 + [_i] * 6 + [_vp, _vp, _vp, _vp, _sz, _vp]),
     "inf3dp_fields_intersection_grid": (_i, [_vp] * 6 + [_i] * 6 + [_vp, _vp, _vp, _vp, _sz, _vp]),
+    "inf3dp_coll_pose": (_i, [_vp, _vp, _vp, _i64, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "inf3dp_coll_inside": (_i, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "inf3dp_coll_pack4": (_i, [_vp, _vp, _i, _i64, _vp, _vp]),
+    "inf3dp_coll_predicate": (_i, [_vp, _vp, _i, _i64, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "inf3dp_coll_push": (_i, [_vp, _i64, _vp, _vp, _vp, _vp]),
+    "inf3dp_coll_alter": (_i, [_vp, _vp, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "inf3dp_coll_gather_x": (_i, [_vp, _i64, _vp, _vp, _vp]),
+    "inf3dp_coll_scatter_grads": (_i, [_vp, _i64, _vp, _vp, _vp, _vp]),
     "inf3dp_grid_queries": (_i, [_i, _f, _i64, _i64, _vp, _vp]),
     "inf3dp_marching_cubes_workspace_bytes": (_sz, [_i, _i, _i]),
     "inf3dp_marching_cubes_count": (_i, [_vp, _i, _i, _i, _f, _vp, _sz, _vp, _vp]),

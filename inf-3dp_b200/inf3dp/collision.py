@@ -3,110 +3,138 @@
 Reference: level_collision.CollTVSDF (level_collision.py:68-255, paper section 5.1) and its wrapper
 collision_evaluation (:259-281).  The reference runs the same sequence through utils.field_query_with_grads /
 level_querying_with_confidence, which build an autograd graph per chunk and bounce every intermediate through host
-tensors (utils.py:232-303); here the five field sweeps are launches of the fused kernels on device-resident,
-mask-compacted point sets.  Same predicates, same Eq. 27, same two-step push and the same
-backward (negated, normalised saved directions times the upstream gradient).
+tensors (utils.py:232-303), and glues them with boolean masks / nonzero / gather / where.  Here the field sweeps are
+launches of the fused SIREN kernels on compact device lists, and every step between two sweeps is ONE fused predicate /
+compaction kernel (csrc/collision.cu, include/inf3dp.h: inf3dp_coll_*).  The SDF gradient is
+queried lazily, only for the points whose result carries it.  Same predicates, same Eq. 27, same two-step push and the
+same backward (negated, normalised saved directions times the upstream gradient).
 """
 from __future__ import annotations
 
 import torch
 import torch.nn.functional as F
 
+from . import _lib
 from .query import _net_of
 
 
-def _value_grad(decoder, x):
-    y, J, _ = _net_of(decoder).query(x, order=1)
-    return y[:, 0], J[:, 0, :]
+def _rows(decoder, x):
+    """(value, grad) rows [n,4] of a single-output field network: the reverse-mode engine's packed output when the network
+    is the flagship configuration, otherwise the generic order-1 query packed with torch."""
+    net = _net_of(decoder)
+    if (getattr(net, "out_features", 0) == 1 and getattr(net, "in_features", 0) == 3 and getattr(net, "type", "") == "sine"
+            and getattr(net, "hidden_features", 0) == 256 and getattr(net, "num_hidden_layers", 0) == 3):
+        return net.query_rows(x)
+    y, J, _ = net.query(x, order=1)
+    return torch.cat([y[:, :1], J[:, 0, :]], dim=1).contiguous()
 
 
-def _value(decoder, x):
-    y, _, _ = _net_of(decoder).query(x, order=0)
-    return y[:, 0]
-
-
-def _levels(level_decoder, xyz_slice):
-    """utils.level_querying_with_confidence (utils.py:269-303): arg-max class of the level MLP."""
+def _logits(level_decoder, x4):
     net = getattr(level_decoder, "model", level_decoder)
-    return net(xyz_slice).argmax(dim=-1)
+    return net(x4).to(torch.float32).contiguous()
+
+
+class _Surface:
+    """Where finished points report: per point (CollTVSDF surface) and / or per waypoint (sweep)."""
+
+    def __init__(self, dev, P=0, Nw=0, per_point=False, per_waypoint=False):
+        z = lambda *shape, dtype=torch.float32: torch.zeros(shape, dtype=dtype, device=dev)
+        self.depth_p = z(P) if per_point else None
+        self.mask_p = z(P, dtype=torch.uint8) if per_point else None
+        self.grads_p = z(P, 3) if per_point else None
+        self.depth_w = z(Nw, dtype=torch.int32) if per_waypoint else None      # IEEE bits of the max depth (depths >= 0)
+        self.hit_w = z(Nw, dtype=torch.uint8) if per_waypoint else None
+
+    def ptrs(self):
+        return [_lib.ptr(t) for t in (self.depth_p, self.mask_p, self.grads_p, self.depth_w, self.hit_w)]
+
+
+@torch.no_grad()
+def _fused_collision(surface, waypts, quats, cloud, Nw, M, sdf_decoder, slice_decoder, level_decoder, num_classes,
+                     current_level_maxslices, current_levels, base_th, want_grads):
+    """level_collision.py:73-237 as six field sweeps glued by the fused predicate / compaction stages of csrc/collision.cu
+    (include/inf3dp.h: inf3dp_coll_*).  `cloud` is the nozzle cloud [M,3] when `quats` [Nw,4] pose it at `waypts` [Nw,3]
+    (the posed cloud [Nw,M,3] is never materialised), or the posed cloud [Nw*M,3] itself when quats is None."""
+    dev = cloud.device
+    L = _lib.lib()
+    P = int(Nw) * int(M)
+    C = int(num_classes)
+    st = lambda: _lib.stream_ptr(dev)
+    e = lambda *shape, dtype=torch.float32: torch.empty(shape, dtype=dtype, device=dev)
+    levels_w = current_levels.to(device=dev, dtype=torch.int32).contiguous()
+    maxsl = current_level_maxslices.to(device=dev, dtype=torch.float32).contiguous()
+    if maxsl.dim() != 2 or maxsl.shape[1] != C or maxsl.shape[0] != Nw or levels_w.numel() != Nw:
+        raise RuntimeError("collision: current_level_maxslices must be [N, num_classes] and current_levels [N]")
+    counters = e(8, dtype=torch.int32)
+    out = surface.ptrs()
+    with torch.cuda.device(dev):
+        cube_x, cube_id = e(max(P, 1), 3), e(max(P, 1), dtype=torch.int32)
+        _lib.check(L.inf3dp_coll_pose(_lib.ptr(waypts), _lib.ptr(quats), _lib.ptr(cloud), Nw, M, float(base_th), _lib.ptr(cube_x),
+                                      _lib.ptr(cube_id), _lib.ptr(counters), *out, st()))
+        n_cube = int(counters[0].item())
+        if n_cube == 0:
+            return
+        # SDF value only: its gradient is needed for the few points whose result carries it, queried lazily below (:100-107)
+        sdf_v, _, _ = _net_of(sdf_decoder).query(cube_x[:n_cube], order=0)
+        in_x, in_id, in_sdf = e(n_cube, 3), e(n_cube, dtype=torch.int32), e(n_cube)
+        _lib.check(L.inf3dp_coll_inside(_lib.ptr(sdf_v), n_cube, _lib.ptr(cube_x), _lib.ptr(cube_id), _lib.ptr(in_x),
+                                        _lib.ptr(in_id), _lib.ptr(in_sdf), _lib.ptr(counters), M, *out, st()))
+        del cube_x, cube_id, sdf_v
+        n_in = int(counters[1].item())
+        if n_in == 0:
+            return
+        rows = _rows(slice_decoder, in_x[:n_in])                                                        # :137
+        x4 = e(n_in, 4)
+        _lib.check(L.inf3dp_coll_pack4(_lib.ptr(in_x), _lib.ptr(rows), 4, n_in, _lib.ptr(x4), st()))
+        logits = _logits(level_decoder, x4)                                                             # :139-142
+        if logits.shape[1] != C:
+            raise RuntimeError(f"collision: the level classifier has {logits.shape[1]} classes, num_classes is {C}")
+        del x4
+        re_x, re_src, re_dist = e(n_in, 3), e(n_in, dtype=torch.int32), e(n_in)
+        grad_src = e(n_in, dtype=torch.int32) if want_grads else None
+        _lib.check(L.inf3dp_coll_predicate(_lib.ptr(rows), _lib.ptr(logits), C, n_in, _lib.ptr(in_x), _lib.ptr(in_id),
+                                           _lib.ptr(in_sdf), _lib.ptr(levels_w), _lib.ptr(maxsl), M, _lib.ptr(re_x),
+                                           _lib.ptr(re_src), _lib.ptr(re_dist), _lib.ptr(grad_src), int(want_grads),
+                                           _lib.ptr(counters), *out, st()))
+        del logits
+        n_re = int(counters[2].item())
+        if n_re > 0:
+            rows2 = _rows(slice_decoder, re_x[:n_re])                                                   # :205
+            push_x = e(n_re, 3)
+            _lib.check(L.inf3dp_coll_push(_lib.ptr(rows2), n_re, _lib.ptr(re_x), _lib.ptr(re_dist), _lib.ptr(push_x), st()))
+            del rows2
+            y2, _, _ = _net_of(slice_decoder).query(push_x, order=0)                                    # :211
+            x4 = e(n_re, 4)
+            _lib.check(L.inf3dp_coll_pack4(_lib.ptr(push_x), _lib.ptr(y2), 1, n_re, _lib.ptr(x4), st()))
+            logits2 = _logits(level_decoder, x4)                                                        # :212-213
+            _lib.check(L.inf3dp_coll_alter(_lib.ptr(y2), _lib.ptr(logits2), C, n_re, _lib.ptr(re_src), _lib.ptr(re_dist),
+                                           _lib.ptr(rows), _lib.ptr(in_id), _lib.ptr(in_sdf), _lib.ptr(levels_w),
+                                           _lib.ptr(maxsl), M, _lib.ptr(grad_src), int(want_grads), _lib.ptr(counters), *out, st()))
+        if want_grads:
+            n_g = int(counters[3].item())
+            if n_g > 0:
+                gx = e(n_g, 3)
+                _lib.check(L.inf3dp_coll_gather_x(_lib.ptr(grad_src), n_g, _lib.ptr(in_x), _lib.ptr(gx), st()))
+                rows3 = _rows(sdf_decoder, gx)
+                _lib.check(L.inf3dp_coll_scatter_grads(_lib.ptr(rows3), n_g, _lib.ptr(grad_src), _lib.ptr(in_id),
+                                                       _lib.ptr(surface.grads_p), st()))
 
 
 @torch.no_grad()
 def tvsdf_collision_forward(nozzle_pcd, sdf_decoder, slice_decoder, level_decoder, num_classes, current_level_maxslices,
                             current_levels, base_th):
     """level_collision.py:73-237.  -> (coll_depths [N,M] >= 0, coll_mask [N,M] bool, coll_grads [N,M,3])."""
+    if not nozzle_pcd.is_cuda:
+        raise RuntimeError("inf3dp: the collision query needs CUDA tensors (no CPU fallback)")
     N, M, _ = nozzle_pcd.shape
     dev = nozzle_pcd.device
     coords = nozzle_pcd.detach().reshape(-1, 3).to(torch.float32).contiguous()
-    P = coords.shape[0]
-    waypt_levels = current_levels.to(dev).long().repeat_interleave(M, dim=0)                       # :84
-    level_maxslices = current_level_maxslices.to(dev).float().repeat_interleave(M, dim=0)          # :85
-    coll_depths = torch.zeros(P, device=dev)
-    coll_grads = torch.zeros_like(coords)
-    coll_mask = torch.zeros(P, dtype=torch.bool, device=dev)
-
-    def finish():
-        return F.relu(-coll_depths).view(N, M), coll_mask.view(N, M), coll_grads.view(N, M, 3)
-
-    cube_mask = ((coords >= -1.0) & (coords <= 1.0)).all(dim=-1)                                   # :92
-    cube_idx = cube_mask.nonzero(as_tuple=True)[0]
-    if cube_idx.numel() == 0:
-        return finish()
-    sdfs = torch.ones(P, device=dev)                                                               # :100
-    sdf_grads = torch.zeros_like(coords)
-    cs, cg = _value_grad(sdf_decoder, coords[cube_idx])
-    sdfs[cube_idx] = cs
-    sdf_grads[cube_idx] = cg
-
-    base = coords[:, 2] < base_th                                                                  # :113-117
-    coll_depths[base] = -0.1
-    coll_grads[base] = torch.tensor([0.0, 0.0, 1.0], device=dev)
-    coll_mask |= base
-
-    inside_idx = (sdfs < 0.0).nonzero(as_tuple=True)[0]                                            # :120
-    if inside_idx.numel() == 0:
-        return finish()
-    in_coords = coords[inside_idx]
-    in_wlevels = waypt_levels[inside_idx]
-    in_maxsl = level_maxslices[inside_idx]
-    in_sdfs, in_sdf_grads = sdfs[inside_idx], sdf_grads[inside_idx]
-    in_wmax = in_maxsl.gather(1, in_wlevels.unsqueeze(-1)).squeeze(-1)
-    in_slice, in_slice_grads = _value_grad(slice_decoder, in_coords)                               # :137
-    in_levels = _levels(level_decoder, torch.cat((in_coords, in_slice.unsqueeze(-1)), dim=1))      # :139-140
-    in_coll = (in_levels < in_wlevels) | ((in_levels == in_wlevels) & (in_slice < in_wmax))        # :143-146
-    sel = in_coll.nonzero(as_tuple=True)[0]
-    if sel.numel() == 0:
-        return finish()
-    c_coords, c_levels = in_coords[sel], in_levels[sel]
-    c_sdfs, c_sdf_grads = in_sdfs[sel], in_sdf_grads[sel]
-    c_slice, c_slice_grads = in_slice[sel], in_slice_grads[sel]
-    c_maxsl, c_wlevels = in_maxsl[sel], in_wlevels[sel]
-    c_wmax = c_maxsl.gather(1, c_wlevels.unsqueeze(-1)).squeeze(-1)
-    c_max_single = c_maxsl.gather(1, c_levels.unsqueeze(-1)).squeeze(-1)                           # :166
-    c_dist = (c_slice - c_max_single) / torch.norm(c_slice_grads, dim=-1)                          # :169 (Eq. 27)
-    c_tvsdf = torch.max(c_sdfs, c_dist)
-    tgt = inside_idx[sel]                                                                          # rows of the flat arrays
-    final_tvsdf, final_grads = c_tvsdf.clone(), c_sdf_grads.clone()
-
-    re = (c_dist > c_sdfs).nonzero(as_tuple=True)[0]                                               # :173
-    if re.numel() > 0:
-        r_coords, r_dist, r_slice_grads = c_coords[re], c_dist[re], c_slice_grads[re]
-        push1 = r_coords + torch.abs(r_dist).unsqueeze(-1) * F.normalize(r_slice_grads, dim=-1)    # :202
-        push1 = torch.clamp(push1, min=-1.0, max=1.0)
-        _, g_push1 = _value_grad(slice_decoder, push1)                                             # :205
-        push = push1 + torch.max(torch.abs(r_dist).unsqueeze(-1) * 0.5, torch.tensor(0.04, device=dev)) * \
-            F.normalize(g_push1, dim=-1)                                                           # :206-207
-        push = torch.clamp(push, min=-1.0, max=1.0)
-        p_slice = _value(slice_decoder, push)                                                      # :211
-        p_levels = _levels(level_decoder, torch.cat((push, p_slice.unsqueeze(-1)), dim=1))
-        r_wlevels, r_wmax = c_wlevels[re], c_wmax[re]
-        alter = (p_levels < r_wlevels) | ((p_slice < r_wmax) & (p_levels == r_wlevels))            # :216-217
-        final_tvsdf[re] = torch.where(alter, c_sdfs[re], r_dist)                                   # :218-219
-        final_grads[re] = torch.where(alter.unsqueeze(-1), c_sdf_grads[re], r_slice_grads)
-    coll_depths[tgt] = final_tvsdf                                                                 # :227-231
-    coll_grads[tgt] = final_grads
-    coll_mask[tgt] = True
-    return finish()
+    if N * M >= 1 << 30:
+        raise RuntimeError("inf3dp: CollTVSDF handles < 2^30 points per call; chunk the waypoints (quat_collision_sweep does)")
+    surf = _Surface(dev, P=N * M, per_point=True)
+    _fused_collision(surf, None, None, coords, N, M, sdf_decoder, slice_decoder, level_decoder, num_classes,
+                     current_level_maxslices, current_levels, base_th, want_grads=True)
+    return surf.depth_p.view(N, M), surf.mask_p.view(N, M).bool(), surf.grads_p.view(N, M, 3)
 
 
 class CollTVSDF(torch.autograd.Function):
@@ -151,9 +179,39 @@ def transform_nozzle_pcd_with_quaternion(nozzle_pcd, waypts, quaternions):
 def quat_collision_sweep(waypts, waypt_levels, current_level_maxslice, nozzle_pcd, quat_decoder, sdf_decoder, slice_decoder,
                          level_decoder, num_classes, base_th, waypoint_chunk=1 << 18):
     """The collision query of level_collision.quat_collision_test (:451-...) for many waypoints, device resident:
-    quaternion field at the waypoints (utils.quat_field_querying) -> posed nozzle clouds -> TV-SDF collision evaluation,
-    in chunks of waypoints (the unit the path shards by).  -> (depth per waypoint = max over its nozzle points [N],
-    waypoint collision mask [N])."""
+    quaternion field at the waypoints (utils.quat_field_querying) -> nozzle cloud posed on the fly -> TV-SDF collision
+    evaluation, in chunks of waypoints (the unit the path shards by).  Neither the posed clouds [N,M,3] nor any [N,M] array
+    is materialised: finished points are reduced per waypoint inside the stage kernels.
+    -> (depth per waypoint = max over its nozzle points [N], waypoint collision mask [N])."""
+    if not waypts.is_cuda:
+        raise RuntimeError("inf3dp: the collision query needs CUDA tensors (no CPU fallback)")
+    n = waypts.shape[0]
+    dev = waypts.device
+    M = nozzle_pcd.shape[0]
+    waypoint_chunk = max(1, min(int(waypoint_chunk), ((1 << 30) - 1) // max(M, 1)))
+    depth = torch.empty(n, device=dev)
+    hit = torch.empty(n, dtype=torch.bool, device=dev)
+    qnet = _net_of(quat_decoder)
+    nozzle = nozzle_pcd.detach().to(torch.float32).contiguous()
+    for h in range(0, n, waypoint_chunk):
+        w = waypts[h:h + waypoint_chunk].detach().to(torch.float32).contiguous()
+        nw = w.shape[0]
+        q, _, _ = qnet.query(w, order=0)
+        surf = _Surface(dev, Nw=nw, per_waypoint=True)
+        _fused_collision(surf, w, q.contiguous(), nozzle, nw, M, sdf_decoder, slice_decoder, level_decoder, num_classes,
+                         current_level_maxslice[h:h + waypoint_chunk], waypt_levels[h:h + waypoint_chunk], base_th,
+                         want_grads=False)
+        depth[h:h + nw] = surf.depth_w.view(torch.float32)
+        hit[h:h + nw] = surf.hit_w.bool()
+    return depth, hit
+
+
+@torch.no_grad()
+def quat_collision_sweep_unfused(waypts, waypt_levels, current_level_maxslice, nozzle_pcd, quat_decoder, sdf_decoder,
+                                 slice_decoder, level_decoder, num_classes, base_th, waypoint_chunk=1 << 16):
+    """The same sweep through the per-point surface (posed clouds materialised, [N,M] results reduced with torch): the
+    composition a caller of the reference would write (utils.transform_nozzle_pcd_with_quaternion + CollTVSDF); kept as the
+    comparator of quat_collision_sweep in tests/."""
     n = waypts.shape[0]
     depth = torch.empty(n, device=waypts.device)
     hit = torch.empty(n, dtype=torch.bool, device=waypts.device)

@@ -23,6 +23,10 @@ def all_gather_rows(local, n_total, group=None):
         return local
     rank = dist.get_rank(group)
     lo, hi, per = shard_range(n_total, rank, world)
+    if local.dtype in (torch.int16, torch.bool, torch.uint16):   # not NCCL dtypes: gather the rows as bytes
+        tail = tuple(local.shape[1:])
+        raw = local.contiguous().view(hi - lo, -1).view(torch.uint8)
+        return all_gather_rows(raw, n_total, group).view(local.dtype).view((n_total,) + tail)
     pad = torch.zeros((per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
     pad[:hi - lo] = local
     out = torch.empty((world * per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)

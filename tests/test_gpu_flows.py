@@ -83,3 +83,44 @@ def test_tvsdf_collision_vs_reference(flows, nets):
     assert np.quantile(cosang, 0.01) >= np.cos(np.radians(0.5))
     assert np.abs(gn[hit] - 1.0).max() <= 1e-5 and (gn[~m] == 0).all()
     assert np.array_equal(wmask.cpu().numpy(), m.any(-1))
+
+
+def test_fused_collision_sweep_vs_per_point_composition(golden, nets):
+    """inf3dp.quat_collision_sweep (nozzle posed inside the first stage kernel, results reduced per waypoint inside the
+    stage kernels, nothing of size [N,M] materialised) against the composition a caller of the reference would write:
+    utils.transform_nozzle_pcd_with_quaternion -> CollTVSDF per point -> max / any per waypoint.  The posed points differ in
+    the last bit (torch's cross / normalize kernels vs the fused pose), so points that sit on a decision boundary may flip:
+    waypoint masks agree on all but a handful of waypoints, depths agree where both flag the waypoint.  Also: cfg 4's real
+    nozzle (data/rect_nozzle_shell.xyz[::10] / 150, 6 419 points, tests/golden/cfg1_golden.npz) on a waypoint slice."""
+    import copy
+    import math
+    import inf3dp
+    sdf, slc, lvl = nets
+    sdf = copy.deepcopy(sdf)
+    with torch.no_grad():
+        sdf.net.net[4][0].bias -= 0.06
+    torch.manual_seed(2048)
+    quat = [inf3dp.SingleBVPNet(type="sine", in_features=3, out_features=o) for o in (1, 1, 1, 1, 4)][4].cuda()
+    g = torch.Generator().manual_seed(11)
+    for n, nozzle in ((20_000, None), (600, "shell")):
+        u, v = torch.rand(n, generator=g) * 2 * math.pi, torch.rand(n, generator=g) * 2 * math.pi
+        way = torch.stack([(0.6 + 0.3 * torch.cos(v)) * torch.cos(u), (0.6 + 0.3 * torch.cos(v)) * torch.sin(u), 0.3 * torch.sin(v)], 1).cuda()
+        levels = ((way[:, 2] + 0.3) / 0.6 * 8).clamp(0, 7).long()
+        maxsl = (torch.rand((n, 8), generator=g) * 0.1 - 0.05).cuda()
+        if nozzle is None:
+            t = torch.linspace(0, 1, 64)
+            noz = (torch.stack([0.5 * t * torch.cos(t * 40), 0.5 * t * torch.sin(t * 40), 0.2 + 4.0 * t], 1) / 150.0 * 20.0).cuda()
+        else:
+            noz = torch.from_numpy(np.load(os.path.join(GOLDEN, "cfg1_golden.npz"))["nozzle_shell_every10_scaled"]).cuda()
+            assert noz.shape == (6419, 3)
+        d1, h1 = inf3dp.quat_collision_sweep(way, levels, maxsl, noz, quat, sdf, slc, lvl, 8, -0.9, waypoint_chunk=7001)
+        d2, h2 = inf3dp.quat_collision_sweep_unfused(way, levels, maxsl, noz, quat, sdf, slc, lvl, 8, -0.9, waypoint_chunk=4096)
+        flips = int((h1 != h2).sum())
+        both = h1 & h2
+        dd = (d1 - d2).abs()[both]
+        print(f"collision sweep n={n} M={noz.shape[0]}: {int(h1.sum())} / {int(h2.sum())} colliding waypoints, {flips} flips, "
+              f"max |d depth| {float(dd.max()) if dd.numel() else 0:.2e}")
+        assert h1.any() and (~h1).any()
+        assert flips <= max(2, 0.001 * n)
+        assert dd.numel() == 0 or float(dd.quantile(0.999)) <= 1e-5
+        assert (d1[~h1] == 0).all() and (d1 >= 0).all()
