@@ -52,6 +52,11 @@ int inf3dp_version(void);
  * Supported: hidden == 256, in_features in {3, 4}, 1 <= out_features <= 64, num_hidden_layers >= 0.
  * ------------------------------------------------------------------------------------------------------- */
 
+/* Forget the host-side header mirror of a packed blob.  Call before the blob's memory is freed or overwritten by anything
+ * other than inf3dp_siren_pack_weights: the library caches blob headers by device address (so that queries never read the
+ * device synchronously), and a different blob later placed at the same address must not meet a stale entry.  Never fails. */
+int inf3dp_siren_release(const void* packed_weights);
+
 /* Size of the packed-weights blob for a configuration (0 if unsupported). */
 size_t inf3dp_siren_packed_bytes(int in_features, int hidden, int num_hidden_layers, int out_features);
 

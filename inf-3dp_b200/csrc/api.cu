@@ -18,9 +18,18 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
-// Host mirror of packed headers so that inf3dp_siren_jet never reads the device blob synchronously.
+// Host mirror of packed headers so that inf3dp_siren_jet never reads the device blob synchronously.  Keyed by the blob's
+// device address: an owner that frees or overwrites a blob calls inf3dp_siren_release so that a later blob at the same
+// address (e.g. a clone of another network) cannot hit a stale header; the map is also bounded.
 static std::mutex g_reg_mu;
 static std::unordered_map<const void*, SirenHeader> g_registry;
+constexpr size_t kMaxRegistryEntries = 4096;
+
+static void registry_put(const void* packed, const SirenHeader& h) {
+    std::lock_guard<std::mutex> lk(g_reg_mu);
+    if (g_registry.size() >= kMaxRegistryEntries) g_registry.clear();   // entries are re-read from the device on demand
+    g_registry[packed] = h;
+}
 
 static int lookup_header(const void* packed, SirenHeader* out) {
     {
@@ -35,8 +44,7 @@ static int lookup_header(const void* packed, SirenHeader* out) {
     SirenHeader h;
     INF3DP_CUDA(cudaMemcpy(&h, packed, sizeof(h), cudaMemcpyDeviceToHost));
     INF3DP_CHECK_ARG(h.magic == kSirenMagic, "packed weights: bad magic (not produced by inf3dp_siren_pack_weights)");
-    std::lock_guard<std::mutex> lk(g_reg_mu);
-    g_registry[packed] = h;
+    registry_put(packed, h);
     *out = h;
     return INF3DP_OK;
 }
@@ -239,8 +247,14 @@ int inf3dp_siren_pack_weights(const float* const* W, const float* const* b, int 
     INF3DP_CUDA(cudaMemcpyAsync(packed, &h, sizeof(h), cudaMemcpyHostToDevice, st));
     // the header copy reads a stack object: make sure it has left the host before returning
     INF3DP_CUDA(cudaStreamSynchronize(st));
+    registry_put(packed, h);
+    return INF3DP_OK;
+}
+
+int inf3dp_siren_release(const void* packed) {
+    if (packed == nullptr) return INF3DP_OK;
     std::lock_guard<std::mutex> lk(g_reg_mu);
-    g_registry[packed] = h;
+    g_registry.erase(packed);
     return INF3DP_OK;
 }
 

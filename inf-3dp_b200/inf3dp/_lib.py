@@ -23,6 +23,7 @@ _vp, _i, _i64, _sz, _f = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c
 SIGNATURES = {
     "inf3dp_last_error": (ctypes.c_char_p, []),
     "inf3dp_version": (_i, []),
+    "inf3dp_siren_release": (_i, [_vp]),
     "inf3dp_siren_packed_bytes": (_sz, [_i, _i, _i, _i]),
     "inf3dp_siren_pack_weights": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _sz, _vp]),
     "inf3dp_siren_jet": (_i, [_vp, _vp, _i64, _i, _vp, _vp, _vp, _i, _vp]),

@@ -48,6 +48,22 @@ class PackedWeights:
         self.blob = None
         self._sig = None
 
+    def _release(self):
+        """The library mirrors blob headers by device address: tell it before this blob's memory can be reused."""
+        if self.blob is not None:
+            try:
+                _lib.lib().inf3dp_siren_release(_lib.ptr(self.blob))
+            except Exception:
+                pass
+            self.blob = None
+
+    def __del__(self):
+        self._release()
+
+    def __deepcopy__(self, memo):
+        # a copied module re-packs on first use (its parameters are new tensors): never share or clone the blob
+        return PackedWeights(*self.cfg, self.activation, self.omega0)
+
     def _signature(self, weights, biases):
         return tuple((t.data_ptr(), t._version, str(t.device)) for t in list(weights) + list(biases))
 
@@ -68,6 +84,7 @@ class PackedWeights:
         n = len(ws)
         wp = (ctypes.c_void_p * n)(*[w.data_ptr() for w in ws])
         bp = (ctypes.c_void_p * n)(*[b.data_ptr() for b in bs])
+        self._release()
         blob = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             _lib.check(L.inf3dp_siren_pack_weights(wp, bp, *self.cfg, self.activation, self.omega0, _lib.ptr(blob),
@@ -76,19 +93,23 @@ class PackedWeights:
         return blob
 
 
-_WORKSPACES = {}
+_WORKSPACES = {}          # (device, stream) -> scratch tensor, least recently used first
+_MAX_WORKSPACES = 8       # 38 MB each: a process that keeps creating streams must not accumulate them
 
 
 def _jet_workspace(dev):
     """Scratch of the reverse-mode engine, one per (device, stream): launches on one stream are ordered, launches
-    on different streams must not share it."""
+    on different streams must not share it.  A small LRU: the oldest entry is dropped beyond _MAX_WORKSPACES (the
+    caching allocator keeps its memory alive until the kernels queued on it have run)."""
     key = (dev.index if dev.index is not None else torch.cuda.current_device(), torch.cuda.current_stream(dev).cuda_stream)
-    ws = _WORKSPACES.get(key)
+    ws = _WORKSPACES.pop(key, None)
     if ws is None:
         with torch.cuda.device(dev):
             nbytes = _lib.lib().inf3dp_siren_jet_workspace_bytes()
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        _WORKSPACES[key] = ws
+        while len(_WORKSPACES) >= _MAX_WORKSPACES:
+            _WORKSPACES.pop(next(iter(_WORKSPACES)))      # allocated on its own stream: the allocator orders its reuse
+    _WORKSPACES[key] = ws
     return ws
 
 

@@ -21,6 +21,12 @@ def _worker(rank, world, port, n):
     assert torch.equal(got, full), (rank, got.shape)
     cnt = all_gather_rows(torch.arange(lo, hi, dtype=torch.int32), n)
     assert torch.equal(cnt, torch.arange(n, dtype=torch.int32))
+    # dtypes NCCL has no collective for travel as bytes: int16 index triples and bool masks of the intersection op
+    idx16 = (torch.arange(n * 6, dtype=torch.int32).view(n, 2, 3) - 7).to(torch.int16)
+    assert torch.equal(all_gather_rows(idx16[lo:hi].clone(), n), idx16)
+    mask = (torch.arange(n * 5).view(n, 5) % 3 == 0)
+    got_mask = all_gather_rows(mask[lo:hi].clone(), n)
+    assert got_mask.dtype == torch.bool and torch.equal(got_mask, mask)
     dist.destroy_process_group()
 
 
