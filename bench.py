@@ -551,6 +551,28 @@ def bench_collision(sdf_net, dev, rank, world, n_waypoints=4_194_304, m_nozzle=6
     if world > 1:
         out.update({"n_gpus": world, "scaling": f"strong: {n_waypoints} waypoints sharded over {world} ranks, NCCL all-gather of the "
                                                  "per-waypoint depth and mask inside the timed region"})
+    # SURVEY.md 8d cfg 4 at its stated nozzle: data/rect_nozzle_shell.xyz[::10] scaled by 1/150 (level_collision.py:301,463,
+    # configs/collision_config.yaml:118) -- M = 6 419 points per waypoint -- on a 65 536-waypoint slice (420 M nozzle points)
+    try:
+        import numpy as np
+        shell = torch.from_numpy(np.load(os.path.join(ROOT, "tests", "golden", "cfg1_golden.npz"))["nozzle_shell_every10_scaled"]).to(dev)
+        nw = 65536
+        a, b, _ = shard_range(nw, rank, world)
+
+        def sweep_shell():
+            d, h = inf3dp.quat_collision_sweep(way[a:b], levels[a:b], maxsl[a:b], shell, quat_net, sdf, slice_net, level, 8, -0.9,
+                                               waypoint_chunk=4096)
+            if world > 1:
+                return all_gather_rows(d, nw), all_gather_rows(h.to(torch.uint8), nw).bool()
+            return d, h
+        ms2, (d2, h2) = _timeit(sweep_shell, dev, 0, 1)
+        ms2 = _max_over_ranks(ms2, dev, world)
+        out["reference_nozzle"] = {"nozzle": "data/rect_nozzle_shell.xyz[::10] / 150 (6419 points, the reference's test nozzle)",
+                                   "waypoints": nw, "nozzle_points_per_waypoint": int(shell.shape[0]), "ms_per_sweep": ms2,
+                                   "waypoints_per_s": nw / (ms2 / 1e3), "nozzle_points_per_s": nw * int(shell.shape[0]) / (ms2 / 1e3),
+                                   "colliding_waypoints": int(h2.sum())}
+    except Exception as e:   # the fixture is committed; never let this optional leg take the headline down
+        out["reference_nozzle"] = {"error": f"{type(e).__name__}: {e}"}
     return out
 
 

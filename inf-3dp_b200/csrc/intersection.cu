@@ -50,7 +50,8 @@ IsectWs carve_isect(void* base, long long voxels, long long cells, int Ns, int N
 // finite ones and never searched: a NaN isovalue is ignored here (the reference would let it hit every voxel,
 // intersection.cu:98 -- a documented divergence on meaningless input).
 __device__ __forceinline__ void rank_sort(const float* __restrict__ iso, int n, float* sorted, int* perm, int* n_finite) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31, nwarps = (blockDim.x >> 5) * gridDim.x;
+    const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     for (int i = warp; i < n; i += nwarps) {
         const float vi = iso[i];
         int less = 0, finite = 0, nan_before = 0;
@@ -73,23 +74,23 @@ __device__ __forceinline__ void rank_sort(const float* __restrict__ iso, int n, 
             if (i == 0) *n_finite = finite;
         }
     }
-    if (n == 0 && threadIdx.x == 0) *n_finite = 0;
+    if (n == 0 && threadIdx.x == 0 && blockIdx.x == 0) *n_finite = 0;
 }
 
-// One block per isovalue array (the three rank sorts run side by side; each stages its array in shared memory).
+// grid (8, 3): blockIdx.y = isovalue array, its 8 blocks split the elements (each stages the array in shared memory).
 __global__ void isect_prep_kernel(const float* s_iso, const float* a_iso, const float* b_iso, int Ns, int N1, int N2,
                                   IsectWs w) {
     extern __shared__ float s_prep[];
-    const int which = blockIdx.x;
+    const int which = blockIdx.y;
     const float* iso = which == 0 ? s_iso : (which == 1 ? a_iso : b_iso);
     const int n = which == 0 ? Ns : (which == 1 ? N1 : N2);
-    if (which == 0 && threadIdx.x < 4) w.hdr[threadIdx.x] = 0;
+    if (which == 0 && blockIdx.x == 0 && threadIdx.x < 4) w.hdr[threadIdx.x] = 0;
     const bool staged = n <= 8192;
     if (staged) {
         for (int i = threadIdx.x; i < n; i += blockDim.x) s_prep[i] = iso[i];
         __syncthreads();
     }
-    rank_sort(staged ? s_prep : iso, n, w.iso_sorted[which], w.iso_perm[which], &w.hdr[4 + which]);
+    rank_sort(staged ? s_prep : iso, n, w.iso_sorted[which], w.iso_perm[which], &w.hdr[4 + which]);   // blocks split the elements
 }
 
 // Winner initialisation (the outputs are initialised by the cell kernel).
@@ -434,7 +435,10 @@ isect_cell_kernel(const FieldSrc src, const float* __restrict__ s_iso, const flo
         idx[3 * c] = (int16_t)is; idx[3 * c + 1] = (int16_t)i1; idx[3 * c + 2] = (int16_t)i2;
         mask[c] = 1;
 #pragma unroll
-        for (int d = 0; d < 3; ++d) pts[3 * c + d] = (float)((double)(ps[d] + pa[d] + pb[d]) / 3.0);  // intersection.cu:203-213
+        // intersection.cu:203-213 divides by the double literal 3.0: float(double(v) / 3.0).  That equals the correctly rounded
+        // single-precision quotient: v / 3 has a periodic binary expansion (or is exact), so the double result never sits
+        // within 2^-53 of a single-precision rounding boundary and the second rounding cannot change the outcome.
+        for (int d = 0; d < 3; ++d) pts[3 * c + d] = __fdiv_rn(ps[d] + pa[d] + pb[d], 3.0f);
     }
 }
 
@@ -460,7 +464,7 @@ int isect_run(const FieldSrc& src, const float* s_iso, const float* a_iso, const
         return INF3DP_EWORKSPACE;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    isect_prep_kernel<<<3, 1024, 8192 * sizeof(float), st>>>(s_iso, a_iso, b_iso, Ns, N1, N2, w);
+    isect_prep_kernel<<<dim3(8, 3), 1024, 8192 * sizeof(float), st>>>(s_iso, a_iso, b_iso, Ns, N1, N2, w);
     INF3DP_LAUNCH_CHECK("isect_prep_kernel");
     const long long quads = (cells + 3) / 4;
     isect_init_kernel<<<(unsigned)((quads + 255) / 256), 256, 0, st>>>(cells, w.winner);
