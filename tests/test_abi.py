@@ -42,3 +42,15 @@ def test_argument_errors_use_return_codes():
     assert L.inf3dp_fields_intersection_workspace_bytes(8, 8, 8, 4, 4, 4) > 0
     with pytest.raises(_lib.Inf3dpError):
         _lib.check(L.inf3dp_principal_curvatures(None, None, -1, None, None, None))
+    # round-2 entry points: argument errors come back as codes, nothing is launched
+    assert L.inf3dp_siren_release(None) == _lib.OK
+    assert L.inf3dp_siren_value_grad_rows_peers(None, None, 5, None, 0, None, None, 0, None) == _lib.EINVAL
+    assert L.inf3dp_extract_isocontours_required_segments(None, 4, None) == 0
+    assert L.inf3dp_coll_pose(None, None, None, 4, 0, 0.0, None, None, None, None, None, None, None, None, None) == _lib.EINVAL
+    assert b"bad sizes" in L.inf3dp_last_error()
+    assert L.inf3dp_coll_pose(None, None, None, 1 << 20, 1 << 12, 0.0, None, None, None, None, None, None, None, None, None) == _lib.EINVAL
+    assert b"2^30" in L.inf3dp_last_error()
+    assert L.inf3dp_coll_inside(None, -1, None, None, None, None, None, None, 1, None, None, None, None, None, None) == _lib.EINVAL
+    assert L.inf3dp_coll_predicate(None, None, 8, 5, None, None, None, None, None, 4, None, None, None, None, 0, None,
+                                   None, None, None, None, None, None) == _lib.EINVAL
+    assert L.inf3dp_coll_pack4(None, None, 1, 0, None, None) == _lib.OK        # n = 0: nothing to do
