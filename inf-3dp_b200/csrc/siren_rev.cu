@@ -585,27 +585,33 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
                             zz[4 * q + 2] = fmaf(cur[4 * q + 2], inv, b.z);
                             zz[4 * q + 3] = fmaf(cur[4 * q + 3], inv, b.w);
                         }
+                        // Only what the next GEMM's operand needs sits in front of the publish; everything else of the slice
+                        // (cosines for the stash, the value's dot product) is done behind it, off the hand-over path.
                         if (g < 2) {
-                            float cc[16];
 #pragma unroll
-                            for (int i = 0; i < 16; i += 2) {
-                                const float s0 = sin_mufu(zz[i]), s1 = sin_mufu(zz[i + 1]);
-                                cc[i] = cos_mufu(zz[i]);
-                                cc[i + 1] = cos_mufu(zz[i + 1]);
-                                split_pack<true>(s0, s1, o[i >> 1], o[8 + (i >> 1)]);
-                            }
+                            for (int i = 0; i < 16; i += 2)
+                                split_pack<true>(sin_mufu(zz[i]), sin_mufu(zz[i + 1]), o[i >> 1], o[8 + (i >> 1)]);
+                            TC_ST16(addr, o);
+                            publish(mi);
                             float4* sp = my_stash + (size_t)((g * 16 + m) * 4) * 128;
 #pragma unroll
                             for (int j = 0; j < 4; ++j)
-                                st_keep4(sp + j * 128, make_float4(cc[4 * j], cc[4 * j + 1], cc[4 * j + 2], cc[4 * j + 3]), stash_keep);
+                                st_keep4(sp + j * 128, make_float4(cos_mufu(zz[4 * j]), cos_mufu(zz[4 * j + 1]), cos_mufu(zz[4 * j + 2]),
+                                                                   cos_mufu(zz[4 * j + 3])), stash_keep);
                         } else {
-                            // last hidden layer: y += w4 . sin z3 ; start the backward sweep with G w4 (.) cos z3
+                            // last hidden layer: start the backward sweep with G w4 (.) cos z3 ; y += w4 . sin z3 behind the publish
+#pragma unroll
+                            for (int i = 0; i < 16; i += 2) {
+                                const float2 w0 = s_w4[16 * m + i], w1 = s_w4[16 * m + i + 1];
+                                split_pack<true>(cos_mufu(zz[i]) * w0.y, cos_mufu(zz[i + 1]) * w1.y, o[i >> 1], o[8 + (i >> 1)]);
+                            }
+                            TC_ST16(addr, o);
+                            publish(mi);
 #pragma unroll
                             for (int i = 0; i < 16; i += 2) {
                                 const float2 w0 = s_w4[16 * m + i], w1 = s_w4[16 * m + i + 1];
                                 acc_y = fmaf(sin_mufu(zz[i]), w0.x, acc_y);
                                 acc_y = fmaf(sin_mufu(zz[i + 1]), w1.x, acc_y);
-                                split_pack<true>(cos_mufu(zz[i]) * w0.y, cos_mufu(zz[i + 1]) * w1.y, o[i >> 1], o[8 + (i >> 1)]);
                             }
                         }
                     } else if (g < 5) {
@@ -625,7 +631,16 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
                         }
 #pragma unroll
                         for (int i = 0; i < 16; i += 2) split_pack<true>(gg[i], gg[i + 1], o[i >> 1], o[8 + (i >> 1)]);
+                        TC_ST16(addr, o);
+                        publish(mi);
                     } else {
+                        // these accumulator columns (region P, slice m) are dead now (cur holds them): the next tile's layer 0
+                        // goes there first, the input-layer gradient of this tile is accumulated behind the publish
+                        if (has_next) {
+                            layer0_slice(m, s_next[0], s_next[1], s_next[2], o);
+                            TC_ST16(addr, o);
+                            publish(mi);
+                        }
                         // input layer: g_0 = (D / S) (.) cos z_0 (recomputed), dy/dx += g_0 W0'
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
@@ -636,12 +651,6 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
                             gy = fmaf(g0, w.y, gy);
                             gz = fmaf(g0, w.z, gz);
                         }
-                        // these accumulator columns (region P, slice m) are dead now: the next tile's layer 0 goes there
-                        if (has_next) layer0_slice(m, s_next[0], s_next[1], s_next[2], o);
-                    }
-                    if (g < 5 || has_next) {
-                        TC_ST16(addr, o);
-                        publish(mi);
                     }
                 }
             }
