@@ -222,8 +222,11 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
             const long long t_begin = clock64();
             for (int it = 0; it < my_units; ++it) {
                 for (int g = 0; g < kGemms; ++g) {
-                    const uint32_t regA = (g & 1) ? regionQ : regionP;
-                    const uint32_t regD = (g & 1) ? regionP : regionQ;
+                    // KIND 1 runs an odd number of GEMMs per unit and fuses the unit boundary: the two halves of tensor memory swap
+                    // roles from unit to unit (the next tile's layer 0 overwrites the accumulator slices of GEMM 2 as they are read)
+                    const int par = (g + (KIND == 1 ? it : 0)) & 1;
+                    const uint32_t regA = par ? regionQ : regionP;
+                    const uint32_t regD = par ? regionP : regionQ;
 #pragma unroll
                     for (int r = 0; r < 4; ++r) {
                         long long t0 = dbg ? clock64() : 0;
@@ -406,38 +409,57 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
         const float sel_v = (live && c == 0) ? 1.f : 0.f, sel_1 = (live && c >= 1 && c <= 3) ? 1.f : 0.f,
                     sel_2 = (live && c >= 4) ? 1.f : 0.f;
         const float* s_w0f = reinterpret_cast<const float*>(sptr + C::kSmemW0);
-        for (int it = 0; it < my_units; ++it) {
+        // layer 0 (FP32) of one 16-feature slice of this lane's jet row: a = sin z, da_i = cos z w_i, d2a_ij = -sin z w_i w_j
+        auto layer0_jet_slice = [&](int m, float qx, float qy, float qz, uint32_t* o) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 2) {
+                float r2[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int f = 16 * m + i + u;
+                    const float4 w = s_w0[f];
+                    const float z0 = fmaf(w.z, qz, fmaf(w.y, qy, fmaf(w.x, qx, w.w)));
+                    const float sn = sin_layer0(z0), cn = cos_mufu(z0);
+                    const float wi = s_w0f[4 * f + ii], wj = s_w0f[4 * f + jj];
+                    r2[u] = sel_v * sn + sel_1 * cn * wi - (sel_2 * kR2) * sn * wi * wj;
+                }
+                split_pack<true>(r2[0], r2[1], o[i >> 1], o[8 + (i >> 1)]);
+            }
+        };
+        auto load_jet_point = [&](int it, int64_t& pt, bool& pvalid, float& px, float& py, float& pz) {
             const int64_t tile = (unit0 + (int64_t)it * unit_stride) * CTAS + rank;
-            const int64_t pt = tile * kTilePts + 3 * quad + pl;
-            const bool pvalid = live && pt < n;
-            float px = 0.f, py = 0.f, pz = 0.f;
+            pt = tile * kTilePts + 3 * quad + pl;
+            pvalid = live && it < my_units && pt < n;
+            px = py = pz = 0.f;
             if (pvalid) { px = x[3 * pt]; py = x[3 * pt + 1]; pz = x[3 * pt + 2]; }
-            // ---- layer 0 (FP32): a = sin z, da_i = cos z w_i, d2a_ij = -sin z w_i w_j ------------------------------------
+        };
+        // The unit boundary is fused as in KIND 0: the first tile's layer 0 is a prologue; every later tile's layer 0 is produced
+        // inside the rounds of the previous tile's LAST epilogue (GEMM 2), slice by slice over the accumulator columns that were
+        // just read -- with three GEMMs per unit that makes the two tensor-memory halves swap roles from unit to unit.
+        int64_t pt;
+        bool pvalid;
+        float px, py, pz;
+        load_jet_point(0, pt, pvalid, px, py, pz);
+        if (my_units > 0) {
 #pragma unroll 1
             for (int mi = 0; mi < 4; ++mi) {
                 const int m = grp + 4 * mi;
                 uint32_t o[16];
-#pragma unroll
-                for (int i = 0; i < 16; i += 2) {
-                    float r2[2];
-#pragma unroll
-                    for (int u = 0; u < 2; ++u) {
-                        const int f = 16 * m + i + u;
-                        const float4 w = s_w0[f];
-                        const float z0 = fmaf(w.z, pz, fmaf(w.y, py, fmaf(w.x, px, w.w)));
-                        const float sn = sin_layer0(z0), cn = cos_mufu(z0);
-                        const float wi = s_w0f[4 * f + ii], wj = s_w0f[4 * f + jj];
-                        r2[u] = sel_v * sn + sel_1 * cn * wi - (sel_2 * kR2) * sn * wi * wj;
-                    }
-                    split_pack<true>(r2[0], r2[1], o[i >> 1], o[8 + (i >> 1)]);
-                }
+                layer0_jet_slice(m, px, py, pz, o);
                 TC_ST16(regionP + lane_off + 16u * (uint32_t)m, o);
                 publish(mi);
             }
+        }
+        for (int it = 0; it < my_units; ++it) {
+            const bool has_next = it + 1 < my_units;
+            int64_t npt;
+            bool nvalid;
+            float nx, ny, nz;
+            load_jet_point(it + 1, npt, nvalid, nx, ny, nz);   // consumed three GEMMs later
             float acc = 0.f;
 #pragma unroll
             for (int g = 0; g < 3; ++g) {
-                const uint32_t regD = (g & 1) ? regionP : regionQ;
+                const uint32_t regD = ((g + it) & 1) ? regionP : regionQ;
                 const float inv = s_misc[g];
                 // out = [value] sin z  +  [first, second] cos z * (own / S)  -  [second] 2^-4 sin z (dz_i / S)(dz_j / S)
                 const float kb = (sel_1 + sel_2) * inv, kc = -(sel_2 * kR2) * inv * inv;
@@ -479,6 +501,13 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
                         TC_ST16(addr, o);
                         publish(mi);
                     } else {
+                        // these accumulator columns are dead now (cur holds them): the next tile's layer 0 goes there first
+                        if (has_next) {
+                            uint32_t o[16];
+                            layer0_jet_slice(m, nx, ny, nz, o);
+                            TC_ST16(addr, o);
+                            publish(mi);
+                        }
 #pragma unroll
                         for (int i = 0; i < 16; ++i) acc = fmaf(outv[i], s_w4[16 * m + i].x, acc);   // linear output layer (FP32)
                     }
@@ -497,6 +526,9 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
                     Hout[9 * pt + 3 * jj + ii] = hv;
                 }
             }
+            // s_part is rewritten only after three more d_full phases, which every epilogue warp (the readers above included)
+            // has to pass first
+            pt = npt; pvalid = nvalid; px = nx; py = ny; pz = nz;
         }
         } else {
         // The unit boundary is fused: the first tile's layer 0 is a prologue, every later tile's layer 0 is produced INSIDE
