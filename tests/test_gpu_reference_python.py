@@ -201,3 +201,65 @@ def test_patch_reference_rebinds_the_class(ref):
         assert out["model_out"].shape == (5, 1) and out["model_in"].requires_grad
     finally:
         modules.SingleBVPNet = original
+
+
+def test_unmodified_collision_evaluation_vs_fused_stages_real_nozzle(ref, cfg1):
+    """BASELINE.json configs[3] at the reference's own nozzle: level_collision.collision_evaluation (level_collision.py:259-281,
+    the UNMODIFIED reference function: CollTVSDF.forward + its utils helpers, staged in oracle/_ref/py) on the reference's
+    networks on torch CUDA, against inf3dp.collision_evaluation (fused predicate / compaction stages, csrc/collision.cu) on the
+    drop-in networks holding the same weights.  Nozzle = data/rect_nozzle_shell.xyz[::10] / 150 (6 419 points,
+    level_collision.py:301,463), posed by the reference's own utils.transform_nozzle_pcd_with_quaternion at 48 waypoints
+    (308 112 nozzle points), plus the backward pass (normalised saved directions)."""
+    if ref is None:
+        pytest.fail("oracle/_ref/py is absent: run `python oracle/build_ref.py` in the build container before gpurun")
+    import copy
+    import importlib
+    import math
+    import inf3dp
+    modules, diff_operators, utils = ref
+    level_collision = importlib.import_module("level_collision")
+    nets = _seeded_reference_nets(modules)
+    sdf_ref, slice_ref, quat_ref = nets["sdf"].cuda(), nets["slice"].cuda(), nets["quat"].cuda()
+    with torch.no_grad():
+        sdf_ref.net.net[4][0].bias -= 0.06       # the random-init SDF is positive everywhere: put half of the cube inside
+    torch.manual_seed(7)
+    level_ref = torch.nn.Sequential(torch.nn.Linear(4, 256), torch.nn.ReLU(), torch.nn.Linear(256, 256), torch.nn.ReLU(),
+                                    torch.nn.Linear(256, 8)).cuda()
+    sdf, slc = _dropin_of(sdf_ref), _dropin_of(slice_ref)
+    level = inf3dp.MLPClassifier(num_classes=8)
+    level.load_state_dict({f"network.{k}": t for k, t in level_ref.state_dict().items()})
+    level.cuda()
+    nozzle = torch.from_numpy(cfg1["nozzle_shell_every10_scaled"]).cuda()
+    g = torch.Generator().manual_seed(3)
+    n = 48
+    u, v = torch.rand(n, generator=g) * 2 * math.pi, torch.rand(n, generator=g) * 2 * math.pi
+    way = torch.stack([(0.6 + 0.3 * torch.cos(v)) * torch.cos(u), (0.6 + 0.3 * torch.cos(v)) * torch.sin(u), 0.3 * torch.sin(v)], 1).cuda()
+    levels = ((way[:, 2] + 0.3) / 0.6 * 8).clamp(0, 7).long()
+    maxsl = (torch.rand((n, 8), generator=g) * 0.1 - 0.05).cuda()
+    quats = utils.quat_field_querying(Decoder(quat_ref), way.cpu(), no_print=True, return_on_cuda=True)
+    pcd = utils.transform_nozzle_pcd_with_quaternion(nozzle, way, quats).contiguous()
+    assert pcd.shape == (n, 6419, 3)
+    p_ref = pcd.clone().requires_grad_(True)
+    d_ref, m_ref, w_ref = level_collision.collision_evaluation(p_ref, Decoder(sdf_ref), Decoder(slice_ref), level_ref, 8, maxsl, levels, -0.9)
+    d_ref.sum().backward()
+    p_our = pcd.clone().requires_grad_(True)
+    d, m, w = inf3dp.collision_evaluation(p_our, sdf, slc, level, 8, maxsl, levels, -0.9)
+    d.sum().backward()
+    mism = int((m != m_ref).sum())
+    both = m & m_ref
+    dd = (d - d_ref).abs()[both]
+    print(f"collision (reference's own function on CUDA vs fused stages): {int(m_ref.sum())} / {int(m.sum())} hits of {m.numel()} points, "
+          f"{mism} mask mismatches, max |d depth| on common hits {float(dd.max()):.2e}")
+    assert m_ref.any() and (~m_ref).any()
+    assert mism <= 2e-4 * m.numel()                        # points on a decision boundary within the engines' ~1e-6 field difference
+    assert float(dd.quantile(0.999)) <= 1e-5 and float(dd.max()) <= 1e-3
+    assert int((w != w_ref).sum()) <= 1
+    gr, go = p_ref.grad[both], p_our.grad[both]
+    has = gr.norm(dim=-1) > 0
+    cosang = torch.nn.functional.cosine_similarity(gr[has], go[has], dim=-1)
+    assert float(cosang.quantile(0.01)) >= math.cos(math.radians(0.5))
+    # and the sweep (nozzle posed inside the first stage kernel, per-waypoint reduction inside the kernels)
+    quat = _dropin_of(quat_ref, 4)
+    dw, hw = inf3dp.quat_collision_sweep(way, levels, maxsl, nozzle, quat, sdf, slc, level, 8, -0.9)
+    assert int((hw != w_ref).sum()) <= 1
+    assert float((dw - d_ref.max(dim=-1).values).abs()[hw & w_ref].max()) <= 1e-4
