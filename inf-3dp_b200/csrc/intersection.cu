@@ -154,13 +154,25 @@ __device__ __forceinline__ int bound_from_guess(const float* __restrict__ sorted
 
 // window of sorted positions with !(iso < mn) && !(iso > mx)   (intersection.cu:98,107,115)
 // first / scale: sorted[0] and (n - 1) / (sorted[n-1] - sorted[0]) (0 when degenerate) for the interpolation guess.
-__device__ __forceinline__ void iso_window(const float* __restrict__ sorted, int n, float first, float scale, float mn,
-                                           float mx, int& lo, int& hi) {
+//
+// `uniform` (established per block by load_tables): the map f(v) = fl(fl(v - first) * scale) sends every table entry j to
+// within kUniTol of j.  f is monotone (each float operation is), so for any bound value m with p = f(m): every entry
+// j < p - kUniTol is < m and every entry j > p + kUniTol is > m.  Unless an integer lies within kUniTol of p, the lower bound
+// (first entry >= m) and the upper bound (first entry > m) are both ceil(p) -- EXACTLY, whatever the rounding of f -- and no
+// table probe is needed; the ~0.2 % of bounds that sit next to an integer take the probing search.  np.linspace isovalue
+// sets (toolpath_utils.py:223) are uniform to ~1e-4; any other set fails the check and always takes the search.
+constexpr float kUniTol = 1e-3f;
+
+__device__ __forceinline__ void iso_window(const float* __restrict__ sorted, int n, float first, float scale, bool uniform,
+                                           float mn, float mx, int& lo, int& hi) {
     if (mn != mn) { lo = 0; hi = n; return; }
     const float gl = (mn - first) * scale, gh = (mx - first) * scale;
+    const bool fast_lo = uniform && fabsf(gl - rintf(gl)) > kUniTol, fast_hi = uniform && fabsf(gh - rintf(gh)) > kUniTol;
     // float -> int conversion saturates and maps NaN to 0: any value is a valid starting point
-    lo = bound_from_guess(sorted, n, __float2int_ru(gl), [mn](float v) { return v < mn; });
-    hi = bound_from_guess(sorted, n, __float2int_rd(gh) + 1, [mx](float v) { return !(v > mx); });
+    if (fast_lo) lo = min(max(__float2int_ru(gl), 0), n);
+    else lo = bound_from_guess(sorted, n, __float2int_ru(gl), [mn](float v) { return v < mn; });
+    if (fast_hi) hi = min(max(__float2int_ru(gh), 0), n);
+    else hi = bound_from_guess(sorted, n, __float2int_rd(gh) + 1, [mx](float v) { return !(v > mx); });
     if (hi < lo) hi = lo;
 }
 
@@ -171,6 +183,7 @@ struct IsoTables {
     const int* perm[3];
     int n[3];   // finite isovalues only
     float first[3], scale[3];   // interpolation guess: position ~ (value - first) * scale
+    bool uniform[3];            // every entry j maps to within kUniTol of j (see iso_window)
 };
 constexpr int kMaxTableEntries = 6000;   // 48 KB of shared memory; larger isovalue sets are probed in global memory
 
@@ -186,18 +199,24 @@ __device__ __forceinline__ IsoTables load_tables(const IsectWs& w, unsigned char
     }
     if (Ns + N1 + N2 > kMaxTableEntries) {
         for (int i = 0; i < 3; ++i) { t.sorted[i] = w.iso_sorted[i]; t.perm[i] = w.iso_perm[i]; }
-        return t;
+    } else {
+        float* fs = reinterpret_cast<float*>(smem);
+        int* ps = reinterpret_cast<int*>(fs + (Ns + N1 + N2));
+        int o = 0;
+        for (int i = 0; i < 3; ++i) {
+            for (int j = threadIdx.x; j < full[i]; j += blockDim.x) { fs[o + j] = w.iso_sorted[i][j]; ps[o + j] = w.iso_perm[i][j]; }
+            t.sorted[i] = fs + o;
+            t.perm[i] = ps + o;
+            o += full[i];
+        }
+        __syncthreads();
     }
-    float* fs = reinterpret_cast<float*>(smem);
-    int* ps = reinterpret_cast<int*>(fs + (Ns + N1 + N2));
-    int o = 0;
-    for (int i = 0; i < 3; ++i) {
-        for (int j = threadIdx.x; j < full[i]; j += blockDim.x) { fs[o + j] = w.iso_sorted[i][j]; ps[o + j] = w.iso_perm[i][j]; }
-        t.sorted[i] = fs + o;
-        t.perm[i] = ps + o;
-        o += full[i];
+    for (int i = 0; i < 3; ++i) {   // uniformity of the finite entries under the SAME map the window search applies
+        bool ok = t.n[i] > 1 && t.scale[i] > 0.f;
+        for (int j = threadIdx.x; j < t.n[i] && ok; j += blockDim.x)
+            ok = fabsf((t.sorted[i][j] - t.first[i]) * t.scale[i] - (float)j) <= kUniTol;
+        t.uniform[i] = __syncthreads_and(ok) != 0;
     }
-    __syncthreads();
     return t;
 }
 
@@ -305,11 +324,11 @@ __device__ __forceinline__ Windows voxel_windows(const VoxelFields& f, const Iso
     if (!min_max8(f.a[0], f.a[1], amn, amx)) return r;  // order of intersection.cu:79-91
     if (!min_max8(f.b[0], f.b[1], bmn, bmx)) return r;
     if (!min_max8(f.s[0], f.s[1], smn, smx)) return r;
-    iso_window(w.sorted[1], N1, w.first[1], w.scale[1], amn, amx, r.a0, r.a1);
+    iso_window(w.sorted[1], N1, w.first[1], w.scale[1], w.uniform[1], amn, amx, r.a0, r.a1);
     if (r.a0 >= r.a1) return r;
-    iso_window(w.sorted[2], N2, w.first[2], w.scale[2], bmn, bmx, r.b0, r.b1);
+    iso_window(w.sorted[2], N2, w.first[2], w.scale[2], w.uniform[2], bmn, bmx, r.b0, r.b1);
     if (r.b0 >= r.b1) return r;
-    iso_window(w.sorted[0], Ns, w.first[0], w.scale[0], smn, smx, r.s0, r.s1);
+    iso_window(w.sorted[0], Ns, w.first[0], w.scale[0], w.uniform[0], smn, smx, r.s0, r.s1);
     if (r.s0 >= r.s1) return r;
     r.any = true;
     return r;
