@@ -347,7 +347,7 @@ isect_elect_kernel(const FieldSrc src, long long voxels, int Ns, int N1, int N2,
     VoxelFields f;
     if (GRID) load_voxel_grid_warp(src, v, v < voxels, f);
     if (v < voxels) {
-        if (!GRID) load_voxel<false, true>(src, v, f);
+        if (!GRID) load_voxel<false, false>(src, v, f);   // cached loads: the two 16-byte halves of a 32-byte row share their sector in L1
         const Windows r = voxel_windows(f, tb);
         if (r.any) {
             hit = true;
