@@ -247,7 +247,7 @@ def test_unmodified_collision_evaluation_vs_fused_stages_real_nozzle(ref, cfg1):
     d.sum().backward()
     mism = int((m != m_ref).sum())
     both = m & m_ref
-    dd = (d - d_ref).abs()[both]
+    dd = (d - d_ref).detach().abs()[both]
     print(f"collision (reference's own function on CUDA vs fused stages): {int(m_ref.sum())} / {int(m.sum())} hits of {m.numel()} points, "
           f"{mism} mask mismatches, max |d depth| on common hits {float(dd.max()):.2e}")
     assert m_ref.any() and (~m_ref).any()
@@ -262,4 +262,4 @@ def test_unmodified_collision_evaluation_vs_fused_stages_real_nozzle(ref, cfg1):
     quat = _dropin_of(quat_ref, 4)
     dw, hw = inf3dp.quat_collision_sweep(way, levels, maxsl, nozzle, quat, sdf, slc, level, 8, -0.9)
     assert int((hw != w_ref).sum()) <= 1
-    assert float((dw - d_ref.max(dim=-1).values).abs()[hw & w_ref].max()) <= 1e-4
+    assert float((dw - d_ref.detach().max(dim=-1).values).abs()[hw & w_ref].max()) <= 1e-4
