@@ -65,6 +65,10 @@ def _fused_collision(surface, waypts, quats, cloud, Nw, M, sdf_decoder, slice_de
     maxsl = current_level_maxslices.to(device=dev, dtype=torch.float32).contiguous()
     if maxsl.dim() != 2 or maxsl.shape[1] != C or maxsl.shape[0] != Nw or levels_w.numel() != Nw:
         raise RuntimeError("collision: current_level_maxslices must be [N, num_classes] and current_levels [N]")
+    if Nw > 0:
+        lo_l, hi_l = torch.aminmax(levels_w)
+        if int(lo_l) < 0 or int(hi_l) >= C:      # the kernels index maxslices[w, level]: the reference's gather would assert
+            raise RuntimeError(f"collision: current_levels must lie in [0, {C}) (got {int(lo_l)} .. {int(hi_l)})")
     counters = e(8, dtype=torch.int32)
     out = surface.ptrs()
     with torch.cuda.device(dev):

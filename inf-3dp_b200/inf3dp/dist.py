@@ -187,7 +187,8 @@ class FusedRowGather:
         fg.finish()                      # barrier: every rank's rows have landed everywhere
         fg.gathered[r]                   # rows of rank r
 
-    mode: "multicast" | "p2p" (what is in use), chosen by `prefer`."""
+    mode: "multicast" | "p2p" (what is in use), chosen by `prefer`.  Every rank must pass the same `n_local` (pad the last
+    shard): the buffers are symmetric, row r of rank k lives at the same offset everywhere."""
 
     def __init__(self, n_local, device, group=None, prefer="multicast"):
         import torch.distributed._symmetric_memory as symm

@@ -124,3 +124,17 @@ def test_fused_collision_sweep_vs_per_point_composition(golden, nets):
         assert flips <= max(2, 0.001 * n)
         assert dd.numel() == 0 or float(dd.quantile(0.999)) <= 1e-5
         assert (d1[~h1] == 0).all() and (d1 >= 0).all()
+
+
+def test_collision_rejects_out_of_range_levels(nets):
+    import inf3dp
+    sdf, slc, lvl = nets
+    pcd = torch.zeros((4, 8, 3), device="cuda")
+    maxsl = torch.zeros((4, 8), device="cuda")
+    with pytest.raises(RuntimeError, match="current_levels"):
+        inf3dp.collision_evaluation(pcd, sdf, slc, lvl, 8, maxsl, torch.tensor([0, 1, 8, 2], device="cuda"), -0.9)
+    with pytest.raises(RuntimeError, match="num_classes"):
+        inf3dp.collision_evaluation(pcd, sdf, slc, lvl, 8, maxsl[:, :5], torch.tensor([0, 1, 2, 3], device="cuda"), -0.9)
+    d, m, w = inf3dp.collision_evaluation(torch.full((4, 8, 3), 5.0, device="cuda"), sdf, slc, lvl, 8, maxsl,
+                                          torch.tensor([0, 1, 2, 3], device="cuda"), -0.9)      # everything outside the cube
+    assert d.shape == (4, 8) and not m.any() and not w.any() and (d == 0).all()
