@@ -36,8 +36,9 @@ enum {
     INF3DP_MODE_SIMT = 1,       /* FP32 CUDA-core kernel: any supported configuration, orders 0..2     */
     INF3DP_MODE_TC_PRECISE = 2, /* tcgen05 tensor cores, FP16 hi/lo split operands (3 MMAs), FP32 acc. */
     INF3DP_MODE_TC_FAST = 3,    /* tcgen05 tensor cores, single FP16 operands (does NOT meet 0.1 deg)  */
-    INF3DP_MODE_TC_REVERSE = 4  /* tcgen05 CTA pairs, reverse-mode value+gradient (out == 1, order == 1),
-                                   FP16 hi/lo split operands; needs the workspace of inf3dp_siren_jet_ws */
+    INF3DP_MODE_TC_REVERSE = 4  /* tcgen05 CTA pairs, reverse-mode value+gradient (out == 1, order == 1) or
+                                   forward-over-reverse value+gradient+Hessian (out == 1, order == 2), FP16
+                                   hi/lo split operands; needs the workspace of inf3dp_siren_jet_ws         */
 };
 
 const char* inf3dp_last_error(void);
@@ -83,7 +84,10 @@ int inf3dp_siren_jet(const void* packed, const float* x, int64_t n, int order, f
  * value+gradient queries of single-output sine networks on the reverse-mode engine (INF3DP_MODE_TC_REVERSE): the
  * same forward + backward sweep the reference's autograd performs (diff_operators.py:128-132), fused in one kernel,
  * half the tensor work of the forward-mode jet.  The scratch holds the cosines of two hidden layers per resident
- * tile (256 KB per SM) between the sweeps. */
+ * tile (256 KB per SM) between the sweeps.  Order-2 queries of such networks (diff_operators.py:6-44 hessian / hessian3d)
+ * then run forward-over-reverse on the same engine -- the point and its three tangents d/dx_i through the same forward +
+ * backward sweep, 32 points per tile, Hessian rows symmetrised -- instead of the 10-row second-order forward jet that
+ * INF3DP_MODE_TC_PRECISE (and AUTO without a workspace) selects. */
 size_t inf3dp_siren_jet_workspace_bytes(void);
 /* Process-wide cap on the SMs the persistent SIREN engines occupy (0 = all, the default).  A multi-GPU caller that overlaps
  * the all-gather of chunk i with the query of chunk i+1 leaves a few SMs to the NCCL kernels (inf3dp/dist.py). */

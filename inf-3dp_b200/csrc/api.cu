@@ -282,6 +282,7 @@ int inf3dp_siren_jet_ws(const void* packed, const float* x, int64_t n, int order
     switch (mode) {
         case INF3DP_MODE_AUTO:
             if (rev_capable && have_ws) return siren_rev_launch(packed, h, x, n, y, J, workspace, workspace_bytes, st);
+            if (jet2_capable && have_ws) return siren_hess_launch(packed, h, x, n, y, J, H, workspace, workspace_bytes, st);
             if (jet2_capable) return siren_jet2_launch(packed, h, x, n, y, J, H, st);
             if (mlp_capable) return siren_mlp_launch(packed, h, x, n, y, st);
             if (tc_capable) return siren_tc_launch(packed, h, x, n, order, y, J, true, st);
@@ -297,8 +298,9 @@ int inf3dp_siren_jet_ws(const void* packed, const float* x, int64_t n, int order
                              "out<=4 and order<=1");
             return siren_tc_launch(packed, h, x, n, order, y, J, mode == INF3DP_MODE_TC_PRECISE, st);
         case INF3DP_MODE_TC_REVERSE:
+            if (jet2_capable) return siren_hess_launch(packed, h, x, n, y, J, H, workspace, workspace_bytes, st);
             INF3DP_CHECK_ARG(rev_capable, "siren_jet: reverse-mode engine needs sine, in=3, hidden=256, 3 hidden layers, "
-                             "out=1 and order=1");
+                             "out=1 and order 1 or 2");
             return siren_rev_launch(packed, h, x, n, y, J, workspace, workspace_bytes, st);
         default:
             set_error("siren_jet: unknown mode %d", mode);

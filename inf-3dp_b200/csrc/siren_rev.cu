@@ -96,6 +96,12 @@ struct RevCfg {
 // KIND 2: the level classifier of the collision query (exp_scripts/train_levels.py:35-51, utils.py:269-303): ReLU MLP
 //         4 -> 256 -> 256 -> C (C <= 16), value only.  One GEMM per tile of 128 points; layer 0 (4 -> 256) and the linear
 //         output layer (256 -> C, folded into the hidden layer's epilogue) are FP32 CUDA-core work.
+// KIND 3: value + gradient + Hessian by FORWARD-over-REVERSE differentiation (diff_operators.py:6-44 builds the same thing
+//         with a second autograd pass): the KIND 0 sweep on a tile of 32 points x 4 rows -- the point itself and its three
+//         tangents d/dx_i carried through the forward AND the backward sweep (6 GEMMs, same weight images).  Row 4p + c of
+//         tensor memory: c = 0 the primal row (a_l, then G g_l), c = 1..3 the tangent rows (da_l/dx_i, then kT G dg_l/dx_i).
+//         The primal row yields (y, dy/dx), tangent row i yields row i of the Hessian.  24 row-GEMMs per point instead of the
+//         30 of the second-order jet, and about half of its epilogue instructions per point.
 // Destinations of the packed (value, grad) rows when the query is fused with the multi-GPU all-gather (KIND 0 only):
 // either one NVLink multicast address (multimem.st, replicated by the switch) or up to 8 peer-mapped buffers.
 constexpr int kMaxRowPeers = 8;
@@ -111,8 +117,8 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
                  float* __restrict__ y, float* __restrict__ J, float* __restrict__ Hout, float4* __restrict__ stash,
                  unsigned long long* __restrict__ dbg, const RowPeers peers) {
     using C = RevCfg<CTAS>;
-    constexpr int kGemms = KIND == 0 ? 6 : (KIND == 1 ? 3 : 1);
-    constexpr int kTilePts = KIND == 1 ? 12 : 128;
+    constexpr int kGemms = (KIND == 0 || KIND == 3) ? 6 : (KIND == 1 ? 3 : 1);
+    constexpr int kTilePts = KIND == 1 ? 12 : (KIND == 3 ? 32 : 128);
     constexpr size_t kImgBase = KIND == 2 ? kMlpOffImg : kRevOffImg;
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t sbase = (smem_u32(smem_dyn) + 1023u) & ~1023u;   // same offset in both CTAs of a pair
@@ -530,6 +536,226 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
             // has to pass first
             pt = npt; pvalid = nvalid; px = nx; py = ny; pz = nz;
         }
+        } else if constexpr (KIND == 3) {
+        // ---------------- forward-over-reverse: 32 points x (primal row + three tangent rows) ------------------------------
+        //   forward   z = a W'^T + b'            a = sin z                 c = cos z
+        //             zt_i = at_i W'^T           at_i = c (.) zt_i         ct_i = -a (.) zt_i                 (tangents d/dx_i)
+        //   backward  g_{l-1}    = (g_l W') (.) c_{l-1}
+        //             gt_{l-1,i} = (gt_{l,i} W') (.) c_{l-1} + (g_l W') (.) ct_{l-1,i}
+        //   input     dy/dx = g_0 W_0' ,  H[i,:] = gt_{0,i} W_0'
+        // Every row stashes ONE float per feature and layer for the backward sweep (primal: c, tangent: ct), so the scratch has
+        // the KIND 0 layout; a tangent row fetches its point's z / c / upstream product from the primal lane by shuffle.
+        const int c = lane & 3;                         // 0: primal row; 1..3: tangent along x_{c-1}
+        const int src = lane & ~3;                      // lane of this point's primal row
+        const int ii = c > 0 ? c - 1 : 0;
+        const float selP = c == 0 ? 1.f : 0.f, selT = c == 0 ? 0.f : 1.f;
+        constexpr float kT = 0.03125f;                  // tangent rows of the backward sweep are carried scaled by 2^-5 (FP16 range)
+        const float kTs = selT * kT;
+        const float phase0 = selT * kHalfPi;            // layer 0: one MUFU per row-feature, cos z = sin(z + pi/2) on tangent rows
+        const float* s_w0f = reinterpret_cast<const float*>(sptr + C::kSmemW0);
+        auto load_point = [&](int it, int64_t& pt, bool& pvalid, float& px, float& py, float& pz) {
+            const int64_t tile = (unit0 + (int64_t)it * unit_stride) * CTAS + rank;
+            pt = tile * kTilePts + (row >> 2);
+            pvalid = it < my_units && pt < n;
+            px = py = pz = 0.f;
+            if (pvalid) { px = x[3 * pt]; py = x[3 * pt + 1]; pz = x[3 * pt + 2]; }
+        };
+        // layer 0 (FP32): a_0 = sin z_0 (primal), da_0/dx_i = cos z_0 W_0'[:, i] (tangent).  The quarter turn is added to the bias
+        // BEFORE the dot product, so the argument carries the same FP32 rounding as z_0 itself and nothing more.
+        auto layer0_slice = [&](int m, float qx, float qy, float qz, uint32_t* o) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 2) {
+                float r2[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int f = 16 * m + i + u;
+                    const float4 w = s_w0[f];
+                    const float z0 = fmaf(w.z, qz, fmaf(w.y, qy, fmaf(w.x, qx, w.w + phase0)));
+                    const float wi = s_w0f[4 * f + ii];
+                    r2[u] = sin_layer0(z0) * (c == 0 ? 1.f : wi);
+                }
+                split_pack<true>(r2[0], r2[1], o[i >> 1], o[8 + (i >> 1)]);
+            }
+        };
+        int64_t pt;
+        bool pvalid;
+        float px, py, pz;
+        load_point(0, pt, pvalid, px, py, pz);
+        if (my_units > 0) {
+#pragma unroll 1
+            for (int mi = 0; mi < 4; ++mi) {
+                const int m = grp + 4 * mi;
+                uint32_t o[16];
+                layer0_slice(m, px, py, pz, o);
+                TC_ST16(regionP + lane_off + 16u * (uint32_t)m, o);
+                publish(mi);
+            }
+        }
+        for (int it = 0; it < my_units; ++it) {
+            float* s_next = reinterpret_cast<float*>(sptr + C::kSmemNext) + 3 * (grp * 128 + row);
+            const bool has_next = it + 1 < my_units;
+            float acc_y = 0.f, gx = 0.f, gy = 0.f, gz = 0.f;
+#pragma unroll
+            for (int g = 0; g < 6; ++g) {
+                const uint32_t regD = (g & 1) ? regionP : regionQ;
+                const float inv = s_misc[g < 3 ? g : 5 - g];              // 1/S of the layer this GEMM multiplies by
+                const float invT = selT * inv;
+                float4 cs[4];                                             // this row's stash of the current slice
+                if (g == 3) {
+                    int64_t npt; bool nvalid; float nx, ny, nz;
+                    load_point(it + 1, npt, nvalid, nx, ny, nz);
+                    s_next[0] = nx; s_next[1] = ny; s_next[2] = nz;
+                }
+                if (g == 3 || g == 4) {
+                    const float4* sp = my_stash + (size_t)(((4 - g) * 16 + grp) * 4) * 128;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) cs[j] = ld_keep4(sp + j * 128, stash_keep);
+                }
+                mbar_wait_warp(bar(C::kBarDFull), dphase, lane, pd);
+                dphase ^= 1u;
+                tc_fence_after();
+                uint32_t v[16];
+                TC_LD16(regD + lane_off + 16u * (uint32_t)grp, v);
+#pragma unroll 1
+                for (int mi = 0; mi < 4; ++mi) {
+                    const int m = grp + 4 * mi;
+                    const uint32_t addr = regD + lane_off + 16u * (uint32_t)m;
+                    tc_wait_ld();
+                    float cur[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) cur[i] = __uint_as_float(v[i]);
+                    if (mi < 3) TC_LD16(addr + 64u, v);
+                    uint32_t o[16];
+                    if (g < 3) {
+                        // forward through layer g + 1
+                        const float4* bp = reinterpret_cast<const float4*>(s_bias + g * 256 + 16 * m);
+                        float av[16], sv[16];                             // next operand / what the backward sweep needs of this layer
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float4 b = bp[q];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const int i = 4 * q + u;
+                                const float zp = __shfl_sync(0xffffffffu, cur[i], src);
+                                const float z = fmaf(zp, inv, u == 0 ? b.x : (u == 1 ? b.y : (u == 2 ? b.z : b.w)));
+                                const float sn = sin_mufu(z), cn = cos_mufu(z);
+                                const float zt = cur[i] * invT;           // tangent rows: dz/dx_i; 0 on the primal row
+                                av[i] = fmaf(cn, zt, selP * sn);          // sin z | cos z dz/dx_i
+                                sv[i] = fmaf(-sn, zt, selP * cn);         // cos z | -sin z dz/dx_i
+                            }
+                        }
+                        if (g < 2) {
+#pragma unroll
+                            for (int i = 0; i < 16; i += 2) split_pack<true>(av[i], av[i + 1], o[i >> 1], o[8 + (i >> 1)]);
+                            TC_ST16(addr, o);
+                            publish(mi);
+                            float4* sp = my_stash + (size_t)((g * 16 + m) * 4) * 128;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                st_keep4(sp + j * 128, make_float4(sv[4 * j], sv[4 * j + 1], sv[4 * j + 2], sv[4 * j + 3]), stash_keep);
+                        } else {
+                            // last hidden layer: the backward sweep starts with G w4 (.) c_3 (primal) and kT G w4 (.) ct_3 (tangents)
+                            const float ks = selP + kTs;
+#pragma unroll
+                            for (int i = 0; i < 16; i += 2) {
+                                const float2 w0 = s_w4[16 * m + i], w1 = s_w4[16 * m + i + 1];
+                                split_pack<true>(sv[i] * (ks * w0.y), sv[i + 1] * (ks * w1.y), o[i >> 1], o[8 + (i >> 1)]);
+                            }
+                            TC_ST16(addr, o);
+                            publish(mi);
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) acc_y = fmaf(av[i], s_w4[16 * m + i].x, acc_y);   // y on the primal row
+                        }
+                    } else if (g < 5) {
+                        // backward through layer 6 - g
+                        float gg[16];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const int i = 4 * j + u;
+                                const float st = u == 0 ? cs[j].x : (u == 1 ? cs[j].y : (u == 2 ? cs[j].z : cs[j].w));
+                                const float own = cur[i] * inv;
+                                const float pc = __shfl_sync(0xffffffffu, st, src);     // the point's cosine
+                                const float pD = __shfl_sync(0xffffffffu, own, src);    // the point's upstream product
+                                gg[i] = fmaf(kTs * pD, st, own * pc);
+                            }
+                        }
+                        if (mi < 3) {
+                            const float4* sp = my_stash + (size_t)(((4 - g) * 16 + m + 4) * 4) * 128;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) cs[j] = ld_keep4(sp + j * 128, stash_keep);
+                        }
+#pragma unroll
+                        for (int i = 0; i < 16; i += 2) split_pack<true>(gg[i], gg[i + 1], o[i >> 1], o[8 + (i >> 1)]);
+                        TC_ST16(addr, o);
+                        publish(mi);
+                    } else {
+                        if (has_next) {
+                            layer0_slice(m, s_next[0], s_next[1], s_next[2], o);
+                            TC_ST16(addr, o);
+                            publish(mi);
+                        }
+                        // input layer: g_0 = (D / S) (.) c_0 [+ kT (D_primal / S) (.) ct_0], c_0 / ct_0 recomputed from the point;
+                        // the primal lane hands -kT (D / S) sin z_0 to its tangents
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const int f = 16 * m + i;
+                            const float4 w = s_w0[f];
+                            const float z0 = fmaf(w.z, pz, fmaf(w.y, py, fmaf(w.x, px, w.w)));
+                            const float own = cur[i] * inv;
+                            const float q = __shfl_sync(0xffffffffu, (own * -kT) * sin_layer0(z0), src);
+                            const float g0 = fmaf(selT * q, s_w0f[4 * f + ii], own * cos_mufu(z0));
+                            gx = fmaf(g0, w.x, gx);
+                            gy = fmaf(g0, w.y, gy);
+                            gz = fmaf(g0, w.z, gz);
+                        }
+                    }
+                }
+            }
+
+            // ---- outputs: sum the four feature-quarter partials of every row in a fixed order ----------------------------
+            s_part[(grp * 4 + 0) * 128 + row] = acc_y;
+            s_part[(grp * 4 + 1) * 128 + row] = gx;
+            s_part[(grp * 4 + 2) * 128 + row] = gy;
+            s_part[(grp * 4 + 3) * 128 + row] = gz;
+            asm volatile("bar.sync 1, 512;" ::: "memory");
+            if (grp == 0) {
+                float r4[4];
+#pragma unroll
+                for (int o = 0; o < 4; ++o)
+                    r4[o] = ((s_part[(0 * 4 + o) * 128 + row] + s_part[(1 * 4 + o) * 128 + row]) +
+                             s_part[(2 * 4 + o) * 128 + row]) + s_part[(3 * 4 + o) * 128 + row];
+                const float inv_g = s_misc[4];
+                // Hessian rows come out of three separate tangent sweeps: symmetrise, H[i][k] = (h_i[k] + h_k[i]) / 2
+                const float hs = inv_g * (1.f / kT);
+                const float hrow[3] = {r4[1] * hs, r4[2] * hs, r4[3] * hs};
+                float other[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const float t0 = __shfl_sync(0xffffffffu, hrow[0], src + 1 + k), t1 = __shfl_sync(0xffffffffu, hrow[1], src + 1 + k),
+                                t2 = __shfl_sync(0xffffffffu, hrow[2], src + 1 + k);
+                    other[k] = ii == 0 ? t0 : (ii == 1 ? t1 : t2);
+                }
+                if (pvalid) {
+                    if (c == 0) {
+                        y[pt] = r4[0] + s_misc[3];
+                        J[3 * pt] = r4[1] * inv_g;
+                        J[3 * pt + 1] = r4[2] * inv_g;
+                        J[3 * pt + 2] = r4[3] * inv_g;
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) Hout[9 * pt + 3 * ii + k] = 0.5f * (hrow[k] + other[k]);
+                    }
+                }
+            }
+            {   // the parked point becomes the current one (hazards into the next unit: as in KIND 0)
+                const int64_t tile = (unit0 + (int64_t)(it + 1) * unit_stride) * CTAS + rank;
+                pt = tile * kTilePts + (row >> 2);
+                pvalid = has_next && pt < n;
+                if (has_next) { px = s_next[0]; py = s_next[1]; pz = s_next[2]; }
+            }
+        }
         } else {
         // The unit boundary is fused: the first tile's layer 0 is a prologue, every later tile's layer 0 is produced INSIDE
         // the rounds of the previous tile's last epilogue (GEMM 5), slice by slice over the accumulator columns that were
@@ -833,7 +1059,7 @@ int launch_rev(const void* packed, const SirenHeader& h, const float* x, int64_t
     auto kern = siren_rev_kernel<CTAS, KIND>;
     const int smem = (int)(KIND == 2 ? C::kSmemTotalMlp : C::kSmemTotal) + 1024;
     INF3DP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    constexpr int kTilePts = KIND == 1 ? 12 : 128;
+    constexpr int kTilePts = KIND == 1 ? 12 : (KIND == 3 ? 32 : 128);
     const int64_t tiles = (n + kTilePts - 1) / kTilePts;
     const int64_t units = (tiles + CTAS - 1) / CTAS;
     const int64_t max_units = siren_sms() / CTAS;
@@ -869,7 +1095,7 @@ int launch_rev(const void* packed, const SirenHeader& h, const float* x, int64_t
                     hbuf[33 + g * 4] / u, hbuf[34 + g * 4] / u, hbuf[35 + g * 4] / u);
         fprintf(stderr, "[inf3dp rev debug] CTAS=%d KIND=%d block0: %.0f units, %.0f cyc/unit (%d GEMMs); MMA thread blocked on a_ready %.0f, "
                         "on w_full %.0f cyc/unit; epilogue warp0 blocked on d_full %.0f, warp5 %.0f, warp15 %.0f cyc/unit\n",
-                CTAS, KIND, u, hbuf[0] / u, KIND == 0 ? 6 : (KIND == 1 ? 3 : 1), hbuf[1] / u, hbuf[2] / u, hbuf[8] / u, hbuf[13] / u, hbuf[23] / u);
+                CTAS, KIND, u, hbuf[0] / u, (KIND == 0 || KIND == 3) ? 6 : (KIND == 1 ? 3 : 1), hbuf[1] / u, hbuf[2] / u, hbuf[8] / u, hbuf[13] / u, hbuf[23] / u);
     }
     return INF3DP_OK;
 }
@@ -979,6 +1205,16 @@ int siren_jet2_launch(const void* packed, const SirenHeader& h, const float* x, 
     static const int ctas = [] { const char* e = getenv("INF3DP_REV_CTAS"); return e && atoi(e) == 1 ? 1 : 2; }();
     return ctas == 1 ? launch_rev<1, 1>(packed, h, x, n, y, J, H, nullptr, stream)
                      : launch_rev<2, 1>(packed, h, x, n, y, J, H, nullptr, stream);
+}
+
+// The same outputs by forward-over-reverse differentiation (KIND 3): needs the reverse engine's scratch.
+int siren_hess_launch(const void* packed, const SirenHeader& h, const float* x, int64_t n, float* y, float* J, float* H,
+                      void* ws, size_t ws_bytes, cudaStream_t stream) {
+    INF3DP_CHECK_ARG(h.rev_ok && h.off_rev != 0, "siren_hess: packed weights carry no reverse-mode section");
+    INF3DP_CHECK_ARG(ws != nullptr && ws_bytes >= siren_rev_workspace_bytes(),
+                     "siren_hess: workspace of %zu bytes needed (inf3dp_siren_jet_workspace_bytes), got %zu",
+                     siren_rev_workspace_bytes(), ws_bytes);
+    return launch_rev<2, 3>(packed, h, x, n, y, J, H, ws, stream);
 }
 
 }  // namespace inf3dp

@@ -124,7 +124,7 @@ def jet(blob, x, order, out_features, mode=None):
     J = torch.empty((n, out_features, 3), dtype=torch.float32, device=dev) if order >= 1 else None
     H = torch.empty((n, out_features, 3, 3), dtype=torch.float32, device=dev) if order >= 2 else None
     m = _lib.MODES[mode or _JET_MODE["mode"]]
-    ws = _jet_workspace(dev) if (order == 1 and out_features == 1 and m in (_lib.MODE_AUTO, _lib.MODE_TC_REVERSE)) else None
+    ws = _jet_workspace(dev) if (order >= 1 and out_features == 1 and m in (_lib.MODE_AUTO, _lib.MODE_TC_REVERSE)) else None
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().inf3dp_siren_jet_ws(_lib.ptr(blob), _lib.ptr(x), n, order, _lib.ptr(y), _lib.ptr(J),
                                                   _lib.ptr(H), m, _lib.ptr(ws), ws.numel() if ws is not None else 0,

@@ -57,10 +57,11 @@ def test_value_only_and_quaternion_out4(golden, engine):
         assert so.angle_deg(J1.cpu().numpy()[:, c], Jr[:, c]).max() <= TOL_ANGLE
 
 
-@pytest.mark.parametrize("engine", ["simt", "tc_precise", "auto"])
+@pytest.mark.parametrize("engine", ["simt", "tc_precise", "tc_reverse", "auto"])
 def test_hessian_and_curvature_vs_reference(golden, engine):
-    """hessian3d / min_max_curvs_and_vectors of the reference (diff_operators.py:27-44, :167-220) vs the order-2 jet:
-    FP32 CUDA-core engine and the tensor-core second-order jet (CTA pairs, 10 jet rows per point)."""
+    """hessian3d / min_max_curvs_and_vectors of the reference (diff_operators.py:27-44, :167-220) vs the order-2 engines:
+    FP32 CUDA cores, the tensor-core second-order forward jet (10 jet rows per point) and the forward-over-reverse sweep
+    (4 rows per point, what AUTO runs)."""
     import inf3dp
     net = _net(golden)
     x = torch.from_numpy(golden["sdf/hess_x"]).cuda()
@@ -271,6 +272,70 @@ def test_order2_tensor_engine_ragged_sizes_vs_oracle(golden, n):
         k = 17
         y2, J2, H2 = net.query(x[k:], order=2, mode="tc_precise")
         assert torch.equal(y2, y[k:]) and torch.equal(J2, J[k:]) and torch.equal(H2, H[k:])
+
+
+@pytest.mark.parametrize("n", [1, 3, 31, 32, 33, 63, 64, 65, 1000, 50021])
+def test_order2_forward_over_reverse_ragged_sizes_vs_oracle(golden, n):
+    """Forward-over-reverse Hessian engine (mode tc_reverse with order 2: tiles are 32 points per CTA, 64 per CTA pair;
+    diff_operators.py:6-44) on ragged batch sizes against the fp64 oracle: value / gradient at the north_star
+    tolerances, Hessian relative Frobenius <= 1e-4 (measured ~4e-5 max), exact symmetry, batch-split invariance, and
+    agreement with the second-order forward jet.  AUTO selects this engine (bit-identical results)."""
+    net = _net(golden)
+    g = torch.Generator().manual_seed(300 + n)
+    x = (torch.rand(n, 3, generator=g) * 2 - 1).cuda()
+    y, J, H = net.query(x, order=2, mode="tc_reverse")
+    assert y.shape == (n, 1) and J.shape == (n, 1, 3) and H.shape == (n, 1, 3, 3)
+    ya, Ja, Ha = net.query(x, order=2)
+    assert torch.equal(ya, y) and torch.equal(Ja, J) and torch.equal(Ha, H)
+    m = min(n, 4096)
+    yo, Jo, Ho = so.siren_jet(layers_from_golden(golden, "sdf"), x[:m].cpu().numpy().astype(np.float64), order=2)
+    assert np.abs(y[:m].cpu().numpy() - yo).max() <= TOL_F
+    assert so.angle_deg(J[:m].cpu().numpy()[:, 0], Jo[:, 0]).max() <= TOL_ANGLE
+    Hn = H.cpu().numpy()[:, 0]
+    rel = np.linalg.norm((Hn[:m] - Ho[:, 0]).reshape(m, -1), axis=1) / np.linalg.norm(Ho[:, 0].reshape(m, -1), axis=1)
+    assert rel.max() <= 1e-4
+    assert np.array_equal(Hn, np.swapaxes(Hn, -1, -2))
+    assert torch.isfinite(H).all()
+    yj, Jj, Hj = net.query(x, order=2, mode="tc_precise")
+    scale = float(Hj.abs().max())
+    assert float((H - Hj).abs().max()) <= 2e-4 * scale and float((y - yj).abs().max()) <= 2e-6
+    if n > 40:
+        k = 17
+        y2, J2, H2 = net.query(x[k:], order=2, mode="tc_reverse")
+        assert torch.equal(y2, y[k:]) and torch.equal(J2, J[k:]) and torch.equal(H2, H[k:])
+
+
+def test_order2_forward_over_reverse_value_gradient_match_the_reverse_engine(golden):
+    """The primal row of the forward-over-reverse sweep runs the reverse engine's arithmetic: its value and gradient agree
+    with an order-1 query to rounding noise, on the golden points and against the reference's golden outputs."""
+    net = _net(golden)
+    x = torch.from_numpy(golden["x"]).cuda()
+    y2, J2, _ = net.query(x, order=2, mode="tc_reverse")
+    y1, J1, _ = net.query(x, order=1, mode="tc_reverse")
+    assert float((y2 - y1).abs().max()) <= 1e-6
+    assert so.angle_deg(J2.cpu().numpy()[:, 0], J1.cpu().numpy()[:, 0]).max() <= 0.01
+    assert np.abs(y2.cpu().numpy() - golden["sdf/y"]).max() <= TOL_F
+    assert so.angle_deg(J2.cpu().numpy()[:, 0], golden["sdf/grad"]).max() <= TOL_ANGLE
+
+
+def test_order2_forward_over_reverse_needs_the_workspace(golden):
+    """INF3DP_MODE_TC_REVERSE with order 2 is refused without the scratch buffer; AUTO without one runs the forward jet."""
+    from inf3dp import _lib
+    net = _net(golden)
+    x = torch.from_numpy(golden["x"]).cuda()
+    ws, bs = net._weights()
+    blob = net._packed.get(ws, bs)
+    n = len(x)
+    y = torch.empty((n, 1), device="cuda"); J = torch.empty((n, 1, 3), device="cuda"); H = torch.empty((n, 1, 3, 3), device="cuda")
+    L = _lib.lib()
+    rc = L.inf3dp_siren_jet_ws(_lib.ptr(blob), _lib.ptr(x), n, 2, _lib.ptr(y), _lib.ptr(J), _lib.ptr(H),
+                               _lib.MODE_TC_REVERSE, None, 0, _lib.stream_ptr(x.device))
+    assert rc == _lib.EINVAL and b"workspace" in L.inf3dp_last_error()
+    rc = L.inf3dp_siren_jet_ws(_lib.ptr(blob), _lib.ptr(x), n, 2, _lib.ptr(y), _lib.ptr(J), _lib.ptr(H),
+                               _lib.MODE_AUTO, None, 0, _lib.stream_ptr(x.device))
+    assert rc == 0
+    _, _, Hj = net.query(x, order=2, mode="tc_precise")
+    assert torch.equal(H, Hj)
 
 
 @pytest.mark.parametrize("gain", [1.0, 3.0, 8.0])
