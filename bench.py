@@ -468,7 +468,7 @@ def bench_intersection(dev, peaks, rank, world, extras):
 
 def bench_hessian_sweep(net, dev, peaks, rank, world):
     """BASELINE.json configs[4]: synthetic 16M-point sweep with Hessian for the min-curvature field (SURVEY.md 8d cfg 5):
-    value + gradient + Hessian from the tensor-core second-order jet, then the closed-form principal curvatures.
+    value + gradient + Hessian from the forward-over-reverse sweep of the CTA-pair engine, then the closed-form principal curvatures.
     N > 1: points sharded, principal curvatures and directions all-gathered (strong scaling)."""
     import torch
     import inf3dp
@@ -492,11 +492,16 @@ def bench_hessian_sweep(net, dev, peaks, rank, world):
         return kap, dirs
     ms, (kap, dirs) = _timeit(sweep, dev, 2, 3)
     ms = _max_over_ranks(ms, dev, world)
-    flop = 3_938_816   # Hessian mode, 1 + 3 + 6 jet columns
-    tf = n * flop / (ms / 1e3) / 1e12
+    flop = 3_938_816        # Hessian mode as a forward jet of 1 + 3 + 6 columns (the figure the survey states)
+    flop_for = 4 * 790_528  # what runs: forward-over-reverse, (1 + 3 tangent) rows x the reverse-mode value+gradient sweep
+    tf, tf_for = n * flop / (ms / 1e3) / 1e12, n * flop_for / (ms / 1e3) / 1e12
     out = {"metric": "siren_value_grad_hessian_curvature_points_per_s", "value": n / (ms / 1e3), "unit": "points/s",
-           "ms_per_sweep": ms, "points": n, "kernel": "siren_rev_kernel<CTAS=2,KIND=1> (forward-mode second-order jet) + principal_curvatures_kernel",
+           "ms_per_sweep": ms, "points": n,
+           "kernel": "siren_rev_kernel<CTAS=2,KIND=3> (forward-over-reverse: primal + 3 tangent rows through the reverse-mode "
+                     "sweep) + principal_curvatures_kernel",
            "flop_per_point": flop, "achieved_tflops": tf, "frac_of_sustained_peak": tf / peaks["tf_sustained"] / world,
+           "flop_per_point_forward_over_reverse": flop_for, "achieved_tflops_forward_over_reverse": tf_for,
+           "frac_of_sustained_peak_forward_over_reverse": tf_for / peaks["tf_sustained"] / world,
            "checksum": float(kap[:: n // 4096].double().sum())}
     if world > 1:
         out.update({"n_gpus": world, "scaling": f"strong: 16 777 216 points sharded over {world} ranks, NCCL all-gather of the "
