@@ -342,7 +342,7 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
                     float r2[2];
 #pragma unroll
                     for (int u = 0; u < 2; ++u) {
-                        const int f = 16 * m + i + u;
+                        const int f = 16 * m + (i >> 1) + 8 * u;   // K-slot pair (i, i + 1) holds features (i / 2, 8 + i / 2)
                         const float4 w = s_w0[f];
                         // x W^T + b in the accumulation order of a row-major dot product (k = 0..3), then the bias
                         const float z = fmaf(w.w, xin.w, fmaf(w.z, xin.z, fmaf(w.y, xin.y, w.x * xin.x))) + s_bias[f];
@@ -422,7 +422,7 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
                 float r2[2];
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
-                    const int f = 16 * m + i + u;
+                    const int f = 16 * m + (i >> 1) + 8 * u;   // K-slot pair (i, i + 1) holds features (i / 2, 8 + i / 2)
                     const float4 w = s_w0[f];
                     const float z0 = fmaf(w.z, qz, fmaf(w.y, qy, fmaf(w.x, qx, w.w)));
                     const float sn = sin_layer0(z0), cn = cos_mufu(z0);
@@ -503,7 +503,7 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
                     if (g < 2) {
                         uint32_t o[16];
 #pragma unroll
-                        for (int i = 0; i < 16; i += 2) split_pack<true>(outv[i], outv[i + 1], o[i >> 1], o[8 + (i >> 1)]);
+                        for (int i = 0; i < 16; i += 2) split_pack<true>(outv[i >> 1], outv[8 + (i >> 1)], o[i >> 1], o[8 + (i >> 1)]);
                         TC_ST16(addr, o);
                         publish(mi);
                     } else {
@@ -568,7 +568,7 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
                 float r2[2];
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
-                    const int f = 16 * m + i + u;
+                    const int f = 16 * m + (i >> 1) + 8 * u;   // K-slot pair (i, i + 1) holds features (i / 2, 8 + i / 2)
                     const float4 w = s_w0[f];
                     const float z0 = fmaf(w.z, qz, fmaf(w.y, qy, fmaf(w.x, qx, w.w + phase0)));
                     const float wi = s_w0f[4 * f + ii];
@@ -651,7 +651,7 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
                         }
                         if (g < 2) {
 #pragma unroll
-                            for (int i = 0; i < 16; i += 2) split_pack<true>(av[i], av[i + 1], o[i >> 1], o[8 + (i >> 1)]);
+                            for (int i = 0; i < 16; i += 2) split_pack<true>(av[i >> 1], av[8 + (i >> 1)], o[i >> 1], o[8 + (i >> 1)]);
                             TC_ST16(addr, o);
                             publish(mi);
                             float4* sp = my_stash + (size_t)((g * 16 + m) * 4) * 128;
@@ -663,8 +663,8 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
                             const float ks = selP + kTs;
 #pragma unroll
                             for (int i = 0; i < 16; i += 2) {
-                                const float2 w0 = s_w4[16 * m + i], w1 = s_w4[16 * m + i + 1];
-                                split_pack<true>(sv[i] * (ks * w0.y), sv[i + 1] * (ks * w1.y), o[i >> 1], o[8 + (i >> 1)]);
+                                const float2 w0 = s_w4[16 * m + (i >> 1)], w1 = s_w4[16 * m + 8 + (i >> 1)];
+                                split_pack<true>(sv[i >> 1] * (ks * w0.y), sv[8 + (i >> 1)] * (ks * w1.y), o[i >> 1], o[8 + (i >> 1)]);
                             }
                             TC_ST16(addr, o);
                             publish(mi);
@@ -695,7 +695,7 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
                             for (int j = 0; j < 4; ++j) cs[j] = ld_keep4(sp + j * 128, stash_keep);
                         }
 #pragma unroll
-                        for (int i = 0; i < 16; i += 2) split_pack<true>(gg[i], gg[i + 1], o[i >> 1], o[8 + (i >> 1)]);
+                        for (int i = 0; i < 16; i += 2) split_pack<true>(gg[i >> 1], gg[8 + (i >> 1)], o[i >> 1], o[8 + (i >> 1)]);
                         TC_ST16(addr, o);
                         publish(mi);
                     } else {
@@ -782,7 +782,7 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
                 float r2[2];
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
-                    const float4 w = s_w0[16 * m + i + u];
+                    const float4 w = s_w0[16 * m + (i >> 1) + 8 * u];
                     r2[u] = sin_layer0(fmaf(w.z, qz, fmaf(w.y, qy, fmaf(w.x, qx, w.w))));
                 }
                 split_pack<true>(r2[0], r2[1], o[i >> 1], o[8 + (i >> 1)]);
@@ -856,7 +856,7 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
                         if (g < 2) {
 #pragma unroll
                             for (int i = 0; i < 16; i += 2)
-                                split_pack<true>(sin_mufu(zz[i]), sin_mufu(zz[i + 1]), o[i >> 1], o[8 + (i >> 1)]);
+                                split_pack<true>(sin_mufu(zz[i >> 1]), sin_mufu(zz[8 + (i >> 1)]), o[i >> 1], o[8 + (i >> 1)]);
                             TC_ST16(addr, o);
                             publish(mi);
                             float4* sp = my_stash + (size_t)((g * 16 + m) * 4) * 128;
@@ -868,8 +868,8 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
                             // last hidden layer: start the backward sweep with G w4 (.) cos z3 ; y += w4 . sin z3 behind the publish
 #pragma unroll
                             for (int i = 0; i < 16; i += 2) {
-                                const float2 w0 = s_w4[16 * m + i], w1 = s_w4[16 * m + i + 1];
-                                split_pack<true>(cos_mufu(zz[i]) * w0.y, cos_mufu(zz[i + 1]) * w1.y, o[i >> 1], o[8 + (i >> 1)]);
+                                const float2 w0 = s_w4[16 * m + (i >> 1)], w1 = s_w4[16 * m + 8 + (i >> 1)];
+                                split_pack<true>(cos_mufu(zz[i >> 1]) * w0.y, cos_mufu(zz[8 + (i >> 1)]) * w1.y, o[i >> 1], o[8 + (i >> 1)]);
                             }
                             TC_ST16(addr, o);
                             publish(mi);
@@ -896,7 +896,7 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
                             for (int j = 0; j < 4; ++j) cs[j] = ld_keep4(sp + j * 128, stash_keep);
                         }
 #pragma unroll
-                        for (int i = 0; i < 16; i += 2) split_pack<true>(gg[i], gg[i + 1], o[i >> 1], o[8 + (i >> 1)]);
+                        for (int i = 0; i < 16; i += 2) split_pack<true>(gg[i >> 1], gg[8 + (i >> 1)], o[i >> 1], o[8 + (i >> 1)]);
                         TC_ST16(addr, o);
                         publish(mi);
                     } else {
@@ -996,8 +996,11 @@ __global__ void rev_pack_gemm_kernel(const float* __restrict__ W, float omega0, 
     const float scale = pow2_scale_to(omega0 * __uint_as_float(*maxabs_bits), 4);   // same S as the forward engine
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= 256 * 256) return;
+    // K slot kb of the image: slots (2c, 2c + 1) of a 16-wide K-step hold features (c, 8 + c) of that step, so that the FP16 hi
+    // word c and lo word 8 + c an epilogue thread writes over the accumulator columns cover exactly the columns they came from
     const int nb = idx >> 8, kb = idx & 255;
-    const float w = transpose ? W[kb * 256 + nb] : W[nb * 256 + kb];
+    const int kf = (kb & ~15) | ((kb & 1) ? 8 + ((kb & 15) >> 1) : ((kb & 15) >> 1));
+    const float w = transpose ? W[kf * 256 + nb] : W[nb * 256 + kf];
     const float v = omega0 * w * scale;
     const __half hi = __float2half_rn(v);
     const __half lo = __float2half_rn(v - __half2float(hi));
