@@ -78,8 +78,9 @@ struct RevCfg {
     static constexpr uint32_t kSmemNext = kSmemPart + 8192;      // float[512][3]: the next tile's point, one slot per epilogue thread
     static constexpr uint32_t kSmemMisc = kSmemNext + 6144;      // inv_scale[3], b4, G, 1/G
     static constexpr uint32_t kSmemBars = kSmemMisc + 64;
-    static constexpr int kBarWFull = 0, kBarWEmpty = kStages, kBarAReady = 2 * kStages, kBarDFull = 2 * kStages + 4,
-                         kNumBars = 2 * kStages + 5;
+    // a_ready: one barrier per operand round (KIND 1, 2: four rounds of four K-steps) or per K-step (KIND 0, 3: sixteen)
+    static constexpr int kBarWFull = 0, kBarWEmpty = kStages, kBarAReady = 2 * kStages, kBarDFull = 2 * kStages + 16,
+                         kNumBars = 2 * kStages + 17;
     static constexpr uint32_t kSmemTmemPtr = kSmemBars + kNumBars * 8;
     static constexpr uint32_t kSmemTotal = kSmemTmemPtr + 16;
     // KIND 2 only: W2^T [256][16] f32 and the partial logits [4 groups][16][128] f32
@@ -120,6 +121,9 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
     constexpr int kGemms = (KIND == 0 || KIND == 3) ? 6 : (KIND == 1 ? 3 : 1);
     constexpr int kTilePts = KIND == 1 ? 12 : (KIND == 3 ? 32 : 128);
     constexpr size_t kImgBase = KIND == 2 ? kMlpOffImg : kRevOffImg;
+    // KIND 0: column-split epilogue -- the four warps of a tensor-memory quadrant share every 16-feature slice (four accumulator
+    // columns each) and publish it K-step by K-step, instead of owning four whole slices each and publishing rounds of four
+    constexpr bool kFine = KIND == 0;
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t sbase = (smem_u32(smem_dyn) + 1023u) & ~1023u;   // same offset in both CTAs of a pair
     unsigned char* sptr = smem_dyn + (sbase - smem_u32(smem_dyn));
@@ -145,7 +149,7 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
             mbar_init(bar(C::kBarWFull + s), (CTAS == 2 && leader) ? 2 : 1);   // own producer (+ the peer's forward)
             mbar_init(bar(C::kBarWEmpty + s), 1);
         }
-        for (int r = 0; r < 4; ++r) mbar_init(bar(C::kBarAReady + r), kEpiWarps * CTAS);
+        for (int r = 0; r < 16; ++r) mbar_init(bar(C::kBarAReady + r), kEpiWarps * CTAS);
         mbar_init(bar(C::kBarDFull), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -236,7 +240,7 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
 #pragma unroll
                     for (int r = 0; r < 4; ++r) {
                         long long t0 = dbg ? clock64() : 0;
-                        mbar_wait<true>(bar(C::kBarAReady + r), aphase);
+                        mbar_wait<true>(bar(C::kBarAReady + (kFine ? kStageK * r : r)), aphase);
                         long long t1 = dbg ? clock64() : 0;
                         mbar_wait<true>(bar(C::kBarWFull + stage), wphase);
                         if (dbg) {
@@ -249,6 +253,15 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
 #pragma unroll
                         for (int tt = 0; tt < kStageK; ++tt) {
                             const int t = kStageK * r + tt;
+                            if (kFine && tt > 0) {
+                                const long long t2 = dbg ? clock64() : 0;
+                                mbar_wait<true>(bar(C::kBarAReady + t), aphase);
+                                tc_fence_after();
+                                if (dbg) {
+                                    wait_a += (unsigned long long)(clock64() - t2);
+                                    if (blockIdx.x == 0) dbg[32 + g * 4 + r] += (unsigned long long)(clock64() - t2);
+                                }
+                            }
                             const uint32_t a_hi = regA + 16u * (uint32_t)t;
                             const uint32_t acc = t > 0 ? 1u : 0u;
                             if (CTAS == 2) {
@@ -314,6 +327,12 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
         unsigned long long wait_d = 0;
         unsigned long long* pd = (dbg && lane == 0) ? &wait_d : nullptr;
 
+        const uint32_t a_ready_base = a_ready_addr[0];                 // barrier of K-step t: + 8 t (one contiguous array)
+        auto publish_step = [&](int t) {   // KIND 0: the columns this warp just stored of K-step t are visible to the MMA issuer
+            tc_wait_st();          // .sync.aligned: the whole warp's stores have completed when any lane gets past it
+            tc_fence_before();
+            if (lane == 0) { if (CTAS == 2) mbar_arrive_cluster(a_ready_base + 8u * (uint32_t)t); else mbar_arrive(a_ready_base + 8u * (uint32_t)t); }
+        };
         auto publish = [&](int mi) {   // the slice just stored is visible to the MMA issuer
             tc_wait_st();
             tc_fence_before();
@@ -776,17 +795,21 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
             px = py = pz = 0.f;
             if (pvalid) { px = x[3 * pt]; py = x[3 * pt + 1]; pz = x[3 * pt + 2]; }
         };
-        auto layer0_slice = [&](int m, float qx, float qy, float qz, uint32_t* o) {   // a0 = sin(W0' x + b0'), FP32
+        // Column split: this warp owns accumulator columns {2 grp, 2 grp + 1, 8 + 2 grp, 9 + 2 grp} of EVERY 16-feature slice t --
+        // with the K-slot order of the weight images those are exactly the columns its FP16 hi words (2 grp, 2 grp + 1) and lo
+        // words (8 + 2 grp, 9 + 2 grp) of K-step t go to.  A slice is complete, and its K-step published, after a quarter of the
+        // math a whole-slice owner needs: the first MMAs of the next GEMM start that much earlier (the hand-over is the engine's
+        // largest idle term), and the last K-step's MMAs are issued as soon as ITS columns are done.
+        const int fa = 2 * grp, fb = 8 + 2 * grp;          // features fa, fa + 1, fb, fb + 1 of a slice; pairs (fa, fb), (fa + 1, fb + 1)
+        auto layer0_cols = [&](int t, float qx, float qy, float qz, uint32_t* o) {   // a0 = sin(W0' x + b0'), FP32
+            float r4[4];
 #pragma unroll
-            for (int i = 0; i < 16; i += 2) {
-                float r2[2];
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    const float4 w = s_w0[16 * m + (i >> 1) + 8 * u];
-                    r2[u] = sin_layer0(fmaf(w.z, qz, fmaf(w.y, qy, fmaf(w.x, qx, w.w))));
-                }
-                split_pack<true>(r2[0], r2[1], o[i >> 1], o[8 + (i >> 1)]);
+            for (int u = 0; u < 4; ++u) {
+                const float4 w = s_w0[16 * t + (u < 2 ? fa + u : fb + u - 2)];
+                r4[u] = sin_layer0(fmaf(w.z, qz, fmaf(w.y, qy, fmaf(w.x, qx, w.w))));
             }
+            split_pack<true>(r4[0], r4[2], o[0], o[2]);    // hi word fa, lo word 8 + fa
+            split_pack<true>(r4[1], r4[3], o[1], o[3]);    // hi word fa + 1, lo word 9 + fa
         };
         int64_t pt;
         bool pvalid;
@@ -794,12 +817,13 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
         load_point(0, pt, pvalid, px, py, pz);
         if (my_units > 0) {
 #pragma unroll 1
-            for (int mi = 0; mi < 4; ++mi) {
-                const int m = grp + 4 * mi;
-                uint32_t o[16];
-                layer0_slice(m, px, py, pz, o);
-                TC_ST16(regionP + lane_off + 16u * (uint32_t)m, o);
-                publish(mi);
+            for (int t = 0; t < 16; ++t) {
+                uint32_t o[4];
+                layer0_cols(t, px, py, pz, o);
+                const uint32_t addr = regionP + lane_off + 16u * (uint32_t)t;
+                TC_ST2(addr + (uint32_t)fa, o[0], o[1]);
+                TC_ST2(addr + (uint32_t)fb, o[2], o[3]);
+                publish_step(t);
             }
         }
         for (int it = 0; it < my_units; ++it) {
@@ -813,104 +837,84 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
             for (int g = 0; g < 6; ++g) {
                 const uint32_t regD = (g & 1) ? regionP : regionQ;
                 const float inv = s_misc[g < 3 ? g : 5 - g];              // 1/S of the layer this GEMM multiplies by
-                float4 cs[4];                                             // stashed cosines of the current slice
+                float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);              // stashed cosines of this warp's columns of the current slice
                 if (g == 3) {   // global-load latency hidden behind two GEMMs
                     int64_t npt; bool nvalid; float nx, ny, nz;
                     load_point(it + 1, npt, nvalid, nx, ny, nz);
                     s_next[0] = nx; s_next[1] = ny; s_next[2] = nz;
                 }
-                if (g == 3 || g == 4) {                                   // issue the first stash read under the wait
-                    const float4* sp = my_stash + (size_t)(((4 - g) * 16 + grp) * 4) * 128;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) cs[j] = ld_keep4(sp + j * 128, stash_keep);
-                }
+                // stash: [layer][slice][grp][128 rows] float4 -- the four cosines of this thread's columns of a slice in one 16-byte
+                // word, written and read by the same thread (coalesced 512 B per warp)
+                if (g == 3 || g == 4) cs = ld_keep4(my_stash + (size_t)(((4 - g) * 16 + 0) * 4 + grp) * 128, stash_keep);
                 mbar_wait_warp(bar(C::kBarDFull), dphase, lane, pd);
                 dphase ^= 1u;
                 tc_fence_after();
-                uint32_t v[16];
-                TC_LD16(regD + lane_off + 16u * (uint32_t)grp, v);
-#pragma unroll 1
-                for (int mi = 0; mi < 4; ++mi) {
-                    const int m = grp + 4 * mi;
-                    const uint32_t addr = regD + lane_off + 16u * (uint32_t)m;
+                uint32_t v[4];
+                TC_LD2(regD + lane_off + (uint32_t)fa, v[0], v[1]);
+                TC_LD2(regD + lane_off + (uint32_t)fb, v[2], v[3]);
+#pragma unroll 4
+                for (int t = 0; t < 16; ++t) {
+                    const uint32_t addr = regD + lane_off + 16u * (uint32_t)t;
                     tc_wait_ld();
-                    float cur[16];
+                    float cur[4];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) cur[i] = __uint_as_float(v[i]);
-                    if (mi < 3) TC_LD16(addr + 64u, v);   // prefetch the next slice (columns 16 (m + 4)) under the math
-                    uint32_t o[16];
+                    for (int i = 0; i < 4; ++i) cur[i] = __uint_as_float(v[i]);    // features fa, fa + 1, fb, fb + 1
+                    if (t < 15) {   // prefetch the next slice's columns under the math
+                        TC_LD2(addr + 16u + (uint32_t)fa, v[0], v[1]);
+                        TC_LD2(addr + 16u + (uint32_t)fb, v[2], v[3]);
+                    }
+                    // Front: what the next GEMM's operand needs.  The K-step is published one slice LATE (after the next slice's
+                    // math, when its tensor-memory store has long completed: no stall on tcgen05.wait::st) -- except the first
+                    // one of a GEMM, which is what the idle tensor pipe is waiting for.
+                    uint32_t o[4];
+                    float zz[4] = {0.f, 0.f, 0.f, 0.f};
+                    float2 wa0 = make_float2(0.f, 0.f), wa1 = wa0, wb0 = wa0, wb1 = wa0;
+                    const bool stores = g < 5 || has_next;
                     if (g < 3) {
                         // forward: z = D / S + b'
-                        const float4* bp = reinterpret_cast<const float4*>(s_bias + g * 256 + 16 * m);
-                        float zz[16];
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const float4 b = bp[q];
-                            zz[4 * q] = fmaf(cur[4 * q], inv, b.x);
-                            zz[4 * q + 1] = fmaf(cur[4 * q + 1], inv, b.y);
-                            zz[4 * q + 2] = fmaf(cur[4 * q + 2], inv, b.z);
-                            zz[4 * q + 3] = fmaf(cur[4 * q + 3], inv, b.w);
-                        }
-                        // Only what the next GEMM's operand needs sits in front of the publish; everything else of the slice
-                        // (cosines for the stash, the value's dot product) is done behind it, off the hand-over path.
+                        const float2 ba = *reinterpret_cast<const float2*>(s_bias + g * 256 + 16 * t + fa);
+                        const float2 bb = *reinterpret_cast<const float2*>(s_bias + g * 256 + 16 * t + fb);
+                        zz[0] = fmaf(cur[0], inv, ba.x); zz[1] = fmaf(cur[1], inv, ba.y);
+                        zz[2] = fmaf(cur[2], inv, bb.x); zz[3] = fmaf(cur[3], inv, bb.y);
                         if (g < 2) {
-#pragma unroll
-                            for (int i = 0; i < 16; i += 2)
-                                split_pack<true>(sin_mufu(zz[i >> 1]), sin_mufu(zz[8 + (i >> 1)]), o[i >> 1], o[8 + (i >> 1)]);
-                            TC_ST16(addr, o);
-                            publish(mi);
-                            float4* sp = my_stash + (size_t)((g * 16 + m) * 4) * 128;
-#pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                st_keep4(sp + j * 128, make_float4(cos_mufu(zz[4 * j]), cos_mufu(zz[4 * j + 1]), cos_mufu(zz[4 * j + 2]),
-                                                                   cos_mufu(zz[4 * j + 3])), stash_keep);
+                            split_pack<true>(sin_mufu(zz[0]), sin_mufu(zz[2]), o[0], o[2]);
+                            split_pack<true>(sin_mufu(zz[1]), sin_mufu(zz[3]), o[1], o[3]);
                         } else {
-                            // last hidden layer: start the backward sweep with G w4 (.) cos z3 ; y += w4 . sin z3 behind the publish
-#pragma unroll
-                            for (int i = 0; i < 16; i += 2) {
-                                const float2 w0 = s_w4[16 * m + (i >> 1)], w1 = s_w4[16 * m + 8 + (i >> 1)];
-                                split_pack<true>(cos_mufu(zz[i >> 1]) * w0.y, cos_mufu(zz[8 + (i >> 1)]) * w1.y, o[i >> 1], o[8 + (i >> 1)]);
-                            }
-                            TC_ST16(addr, o);
-                            publish(mi);
-#pragma unroll
-                            for (int i = 0; i < 16; i += 2) {
-                                const float2 w0 = s_w4[16 * m + i], w1 = s_w4[16 * m + i + 1];
-                                acc_y = fmaf(sin_mufu(zz[i]), w0.x, acc_y);
-                                acc_y = fmaf(sin_mufu(zz[i + 1]), w1.x, acc_y);
-                            }
+                            // last hidden layer: start the backward sweep with G w4 (.) cos z3
+                            wa0 = s_w4[16 * t + fa]; wa1 = s_w4[16 * t + fa + 1]; wb0 = s_w4[16 * t + fb]; wb1 = s_w4[16 * t + fb + 1];
+                            split_pack<true>(cos_mufu(zz[0]) * wa0.y, cos_mufu(zz[2]) * wb0.y, o[0], o[2]);
+                            split_pack<true>(cos_mufu(zz[1]) * wa1.y, cos_mufu(zz[3]) * wb1.y, o[1], o[3]);
                         }
                     } else if (g < 5) {
                         // backward through layer 6-g: g_{l-1} = (D / S) (.) cos z_{l-1}   (cosines from the stash)
-                        float gg[16];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            gg[4 * j] = cur[4 * j] * inv * cs[j].x;
-                            gg[4 * j + 1] = cur[4 * j + 1] * inv * cs[j].y;
-                            gg[4 * j + 2] = cur[4 * j + 2] * inv * cs[j].z;
-                            gg[4 * j + 3] = cur[4 * j + 3] * inv * cs[j].w;
-                        }
-                        if (mi < 3) {
-                            const float4* sp = my_stash + (size_t)(((4 - g) * 16 + m + 4) * 4) * 128;
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) cs[j] = ld_keep4(sp + j * 128, stash_keep);
-                        }
-#pragma unroll
-                        for (int i = 0; i < 16; i += 2) split_pack<true>(gg[i >> 1], gg[8 + (i >> 1)], o[i >> 1], o[8 + (i >> 1)]);
-                        TC_ST16(addr, o);
-                        publish(mi);
-                    } else {
-                        // these accumulator columns (region P, slice m) are dead now (cur holds them): the next tile's layer 0
-                        // goes there first, the input-layer gradient of this tile is accumulated behind the publish
-                        if (has_next) {
-                            layer0_slice(m, s_next[0], s_next[1], s_next[2], o);
-                            TC_ST16(addr, o);
-                            publish(mi);
-                        }
+                        const float gg[4] = {cur[0] * inv * cs.x, cur[1] * inv * cs.y, cur[2] * inv * cs.z, cur[3] * inv * cs.w};
+                        if (t < 15) cs = ld_keep4(my_stash + (size_t)(((4 - g) * 16 + t + 1) * 4 + grp) * 128, stash_keep);
+                        split_pack<true>(gg[0], gg[2], o[0], o[2]);
+                        split_pack<true>(gg[1], gg[3], o[1], o[3]);
+                    } else if (has_next) {
+                        // these accumulator columns (region P, slice t) are dead now (cur holds them): the next tile's layer 0 goes there
+                        layer0_cols(t, s_next[0], s_next[1], s_next[2], o);
+                    }
+                    if (stores) {
+                        if (t >= 2) publish_step(t - 1);
+                        TC_ST2(addr + (uint32_t)fa, o[0], o[1]);
+                        TC_ST2(addr + (uint32_t)fb, o[2], o[3]);
+                        if (t == 0) publish_step(0);
+                    }
+                    // Back: everything else of the slice, off the hand-over path.
+                    if (g < 2) {
+                        st_keep4(my_stash + (size_t)((g * 16 + t) * 4 + grp) * 128,
+                                 make_float4(cos_mufu(zz[0]), cos_mufu(zz[1]), cos_mufu(zz[2]), cos_mufu(zz[3])), stash_keep);
+                    } else if (g == 2) {
+                        acc_y = fmaf(sin_mufu(zz[0]), wa0.x, acc_y);   // y += w4 . sin z3
+                        acc_y = fmaf(sin_mufu(zz[1]), wa1.x, acc_y);
+                        acc_y = fmaf(sin_mufu(zz[2]), wb0.x, acc_y);
+                        acc_y = fmaf(sin_mufu(zz[3]), wb1.x, acc_y);
+                    } else if (g == 5) {
                         // input layer: g_0 = (D / S) (.) cos z_0 (recomputed), dy/dx += g_0 W0'
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            const float4 w = s_w0[16 * m + i];
+                        for (int i = 0; i < 4; ++i) {
+                            const float4 w = s_w0[16 * t + (i < 2 ? fa + i : fb + i - 2)];
                             const float z0 = fmaf(w.z, pz, fmaf(w.y, py, fmaf(w.x, px, w.w)));
                             const float g0 = cur[i] * inv * cos_mufu(z0);
                             gx = fmaf(g0, w.x, gx);
@@ -919,6 +923,7 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
                         }
                     }
                 }
+                if (g < 5 || has_next) publish_step(15);
             }
 
             // ---- outputs: sum the four feature-quarter partials of every point in a fixed order -------------------

@@ -130,6 +130,11 @@ __host__ __device__ constexpr uint32_t make_idesc(int n) {
                    "=r"(v[15])                                                                                   \
                  : "r"(addr) : "memory")
 
+#define TC_LD2(addr, v0, v1)                                                                                      \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(v0), "=r"(v1) : "r"(addr) : "memory")
+#define TC_ST2(addr, v0, v1)                                                                                      \
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" ::"r"(addr), "r"(v0), "r"(v1) : "memory")
+
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
