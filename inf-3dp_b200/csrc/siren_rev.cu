@@ -61,13 +61,15 @@ constexpr size_t kMlpSectionBytes = kMlpOffImg + 2 * 16 * 8192;
 constexpr int kMlpMaxOut = 16;
 
 constexpr int kEpiWarps = 16;
-constexpr int kProducerWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;
+constexpr int kProducerWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1, kFirstEpiWarp = 0;
 constexpr int kThreads = (kEpiWarps + 2) * 32;  // 576
 constexpr int kStageK = 4;                       // K-steps per ring stage
 constexpr size_t kStashBytesPerCta = 2 * 16 * 4 * 128 * 16;  // [2 layers][16 slices][4][128 rows] float4 = 256 KB
 
-template <int CTAS>
+template <int CTAS, int KIND = 0>
 struct RevCfg {
+    // weight ring: 32 KB stages of four K-steps (a six-stage ring was measured: 494 instead of 504 Mpts/s on the 512^3 grid, the
+    // MMA thread's wait for weights unchanged -- it is the peer CTA's relay, not the depth)
     static constexpr int kStages = CTAS == 2 ? 4 : 3;
     static constexpr uint32_t kStageBytes = (uint32_t)(kStageK * kPerKBytes) * (CTAS == 2 ? 1u : 2u);
     static constexpr uint32_t kSmemRing = 0;
@@ -87,7 +89,7 @@ struct RevCfg {
     static constexpr uint32_t kSmemMlpW2 = (kSmemTotal + 255u) & ~255u;
     static constexpr uint32_t kSmemMlpPart = kSmemMlpW2 + 16384;
     static constexpr uint32_t kSmemTotalMlp = kSmemMlpPart + 32768;
-    static_assert(CTAS == 1 || kSmemTotalMlp <= 232448 - 1024, "shared memory budget");   // KIND 2 runs on CTA pairs only
+    static_assert(CTAS == 1 || (KIND == 2 ? kSmemTotalMlp : kSmemTotal) <= 232448 - 1024, "shared memory budget");   // KIND 2 runs on CTA pairs only
 };
 
 // KIND 0: reverse-mode value + gradient (6 GEMMs per tile of 128 points).
@@ -117,7 +119,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __restrict__ x, int64_t n,
                  float* __restrict__ y, float* __restrict__ J, float* __restrict__ Hout, float4* __restrict__ stash,
                  unsigned long long* __restrict__ dbg, const RowPeers peers) {
-    using C = RevCfg<CTAS>;
+    using C = RevCfg<CTAS, KIND>;
     constexpr int kGemms = (KIND == 0 || KIND == 3) ? 6 : (KIND == 1 ? 3 : 1);
     constexpr int kTilePts = KIND == 1 ? 12 : (KIND == 3 ? 32 : 128);
     constexpr size_t kImgBase = KIND == 2 ? kMlpOffImg : kRevOffImg;
@@ -149,7 +151,7 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
             mbar_init(bar(C::kBarWFull + s), (CTAS == 2 && leader) ? 2 : 1);   // own producer (+ the peer's forward)
             mbar_init(bar(C::kBarWEmpty + s), 1);
         }
-        for (int r = 0; r < 16; ++r) mbar_init(bar(C::kBarAReady + r), kEpiWarps * CTAS);
+        for (int r = 0; r < 16; ++r) mbar_init(bar(C::kBarAReady + r), (kFine ? kEpiWarps / 2 : kEpiWarps) * CTAS);
         mbar_init(bar(C::kBarDFull), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -224,8 +226,8 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
             }
         }
     } else if (warp == kMmaWarp) {
-        if (lane == 0 && leader) {
-            // ================= MMA issuer (leader CTA only) ===========================================================
+        if (leader) {
+            // ================= MMA issuer (leader CTA only): the WHOLE warp runs the loop convergently, one elected lane issues ====
             constexpr uint32_t idesc = CTAS == 2 ? make_idesc_mn(256, 256) : make_idesc_mn(128, 128);
             uint32_t stage = 0, wphase = 0, aphase = 0;
             unsigned long long wait_a = 0, wait_w = 0;
@@ -246,7 +248,7 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
                         if (dbg) {
                             wait_a += (unsigned long long)(t1 - t0);
                             wait_w += (unsigned long long)(clock64() - t1);
-                            if (blockIdx.x == 0) dbg[32 + g * 4 + r] += (unsigned long long)(t1 - t0);
+                            if (blockIdx.x == 0 && lane == 0) dbg[32 + g * 4 + r] += (unsigned long long)(t1 - t0);
                         }
                         tc_fence_after();
                         const uint32_t ring = sbase + C::kSmemRing + stage * C::kStageBytes;
@@ -259,17 +261,18 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
                                 tc_fence_after();
                                 if (dbg) {
                                     wait_a += (unsigned long long)(clock64() - t2);
-                                    if (blockIdx.x == 0) dbg[32 + g * 4 + r] += (unsigned long long)(clock64() - t2);
+                                    if (blockIdx.x == 0 && lane == 0) dbg[32 + g * 4 + r] += (unsigned long long)(clock64() - t2);
                                 }
                             }
+                            if (dbg && blockIdx.x == 0 && it == 4 && lane == 0) dbg[64 + g * 16 + t] = (unsigned long long)clock64();   // K-step t issued
                             const uint32_t a_hi = regA + 16u * (uint32_t)t;
                             const uint32_t acc = t > 0 ? 1u : 0u;
                             if (CTAS == 2) {
                                 const uint32_t sb = ring + (uint32_t)tt * (uint32_t)kPerKBytes;
                                 const uint64_t bh = make_desc(sb, 2048, 128), bl = make_desc(sb + 4096u, 2048, 128);
-                                mma_ts_pair(regD, a_hi, bh, idesc, acc);
-                                mma_ts_pair(regD, a_hi + 8u, bh, idesc, 1u);
-                                mma_ts_pair(regD, a_hi, bl, idesc, 1u);
+                                mma_ts_pair_elect(regD, a_hi, bh, idesc, acc);
+                                mma_ts_pair_elect(regD, a_hi + 8u, bh, idesc, 1u);
+                                mma_ts_pair_elect(regD, a_hi, bl, idesc, 1u);
                             } else {
 #pragma unroll
                                 for (int hf = 0; hf < 2; ++hf) {
@@ -277,20 +280,20 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
                                                         (uint32_t)tt * (uint32_t)kPerKBytes;
                                     const uint64_t bh = make_desc(sb, 2048, 128), bl = make_desc(sb + 4096u, 2048, 128);
                                     const uint32_t d = regD + 128u * (uint32_t)hf;
-                                    mma_ts(d, a_hi, bh, idesc, acc);
-                                    mma_ts(d, a_hi + 8u, bh, idesc, 1u);
-                                    mma_ts(d, a_hi, bl, idesc, 1u);
+                                    mma_ts_elect(d, a_hi, bh, idesc, acc);
+                                    mma_ts_elect(d, a_hi + 8u, bh, idesc, 1u);
+                                    mma_ts_elect(d, a_hi, bl, idesc, 1u);
                                 }
                             }
                         }
-                        if (CTAS == 2) tc_commit_pair(bar(C::kBarWEmpty + stage), 3); else tc_commit(bar(C::kBarWEmpty + stage));
+                        if (CTAS == 2) tc_commit_pair_elect(bar(C::kBarWEmpty + stage), 3); else tc_commit_elect(bar(C::kBarWEmpty + stage));
                         if (++stage == C::kStages) { stage = 0; wphase ^= 1u; }
                     }
-                    if (CTAS == 2) tc_commit_pair(bar(C::kBarDFull), 3); else tc_commit(bar(C::kBarDFull));
+                    if (CTAS == 2) tc_commit_pair_elect(bar(C::kBarDFull), 3); else tc_commit_elect(bar(C::kBarDFull));
                     aphase ^= 1u;
                 }
             }
-            if (dbg && blockIdx.x == 0) {
+            if (dbg && blockIdx.x == 0 && lane == 0) {
                 dbg[0] = (unsigned long long)(clock64() - t_begin);
                 dbg[1] = wait_a;
                 dbg[2] = wait_w;
@@ -310,7 +313,7 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
     } else {
         // ================= epilogue warps 0..15 ========================================================================
         const int quad = warp & 3;           // TMEM lane quadrant this warp may access
-        const int grp = warp >> 2;           // slices grp, grp+4, grp+8, grp+12 (one MMA K-step each)
+        const int grp = (warp - kFirstEpiWarp) >> 2;   // slices grp, grp+4, grp+8, grp+12 (one MMA K-step each)
         const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
         const int row = quad * 32 + lane;    // TMEM lane = point of the tile
         const float4* s_w0 = reinterpret_cast<const float4*>(sptr + C::kSmemW0);
@@ -795,21 +798,24 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
             px = py = pz = 0.f;
             if (pvalid) { px = x[3 * pt]; py = x[3 * pt + 1]; pz = x[3 * pt + 2]; }
         };
-        // Column split: this warp owns accumulator columns {2 grp, 2 grp + 1, 8 + 2 grp, 9 + 2 grp} of EVERY 16-feature slice t --
-        // with the K-slot order of the weight images those are exactly the columns its FP16 hi words (2 grp, 2 grp + 1) and lo
-        // words (8 + 2 grp, 9 + 2 grp) of K-step t go to.  A slice is complete, and its K-step published, after a quarter of the
-        // math a whole-slice owner needs: the first MMAs of the next GEMM start that much earlier (the hand-over is the engine's
-        // largest idle term), and the last K-step's MMAs are issued as soon as ITS columns are done.
-        const int fa = 2 * grp, fb = 8 + 2 * grp;          // features fa, fa + 1, fb, fb + 1 of a slice; pairs (fa, fb), (fa + 1, fb + 1)
+        // Column split: two warps share a 16-feature slice.  This warp owns accumulator columns ca .. ca + 3 and cb .. cb + 3
+        // (ca = 4 (grp & 1), cb = 8 + ca) of the slices t = 2 j + (grp >> 1), j = 0 .. 7 -- with the K-slot order of the weight images
+        // those are exactly the columns its FP16 hi words (ca ..) and lo words (cb ..) of K-step t go to.  A slice is complete, and
+        // its K-step published, after half of the math a whole-slice owner needs, two slices at a time: the first MMAs of the
+        // next GEMM start that much earlier (the hand-over is the engine's largest idle term), and the MMAs of the last K-steps are
+        // issued as soon as THEIR columns are done instead of after a round of four.
+        const int ca = 4 * (grp & 1), cb = 8 + ca, tp = grp >> 1;
         auto layer0_cols = [&](int t, float qx, float qy, float qz, uint32_t* o) {   // a0 = sin(W0' x + b0'), FP32
-            float r4[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const float4 w = s_w0[16 * t + (u < 2 ? fa + u : fb + u - 2)];
-                r4[u] = sin_layer0(fmaf(w.z, qz, fmaf(w.y, qy, fmaf(w.x, qx, w.w))));
+            for (int i = 0; i < 4; ++i) {
+                float r2[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const float4 w = s_w0[16 * t + (u ? cb : ca) + i];
+                    r2[u] = sin_layer0(fmaf(w.z, qz, fmaf(w.y, qy, fmaf(w.x, qx, w.w))));
+                }
+                split_pack<true>(r2[0], r2[1], o[i], o[4 + i]);    // hi word ca + i, lo word cb + i
             }
-            split_pack<true>(r4[0], r4[2], o[0], o[2]);    // hi word fa, lo word 8 + fa
-            split_pack<true>(r4[1], r4[3], o[1], o[3]);    // hi word fa + 1, lo word 9 + fa
         };
         int64_t pt;
         bool pvalid;
@@ -817,12 +823,13 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
         load_point(0, pt, pvalid, px, py, pz);
         if (my_units > 0) {
 #pragma unroll 1
-            for (int t = 0; t < 16; ++t) {
-                uint32_t o[4];
+            for (int j = 0; j < 8; ++j) {
+                const int t = 2 * j + tp;
+                uint32_t o[8];
                 layer0_cols(t, px, py, pz, o);
                 const uint32_t addr = regionP + lane_off + 16u * (uint32_t)t;
-                TC_ST2(addr + (uint32_t)fa, o[0], o[1]);
-                TC_ST2(addr + (uint32_t)fb, o[2], o[3]);
+                TC_ST4(addr + (uint32_t)ca, o);
+                TC_ST4(addr + (uint32_t)cb, (o + 4));
                 publish_step(t);
             }
         }
@@ -837,84 +844,100 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
             for (int g = 0; g < 6; ++g) {
                 const uint32_t regD = (g & 1) ? regionP : regionQ;
                 const float inv = s_misc[g < 3 ? g : 5 - g];              // 1/S of the layer this GEMM multiplies by
-                float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);              // stashed cosines of this warp's columns of the current slice
+                float4 csa = make_float4(0.f, 0.f, 0.f, 0.f), csb = csa;  // stashed cosines of this warp's columns of the current slice
                 if (g == 3) {   // global-load latency hidden behind two GEMMs
                     int64_t npt; bool nvalid; float nx, ny, nz;
                     load_point(it + 1, npt, nvalid, nx, ny, nz);
                     s_next[0] = nx; s_next[1] = ny; s_next[2] = nz;
                 }
-                // stash: [layer][slice][grp][128 rows] float4 -- the four cosines of this thread's columns of a slice in one 16-byte
-                // word, written and read by the same thread (coalesced 512 B per warp)
-                if (g == 3 || g == 4) cs = ld_keep4(my_stash + (size_t)(((4 - g) * 16 + 0) * 4 + grp) * 128, stash_keep);
+                // stash: [layer][slice][4][128 rows] float4 -- words 2 (grp & 1) and 2 (grp & 1) + 1 of a slice hold the cosines of this
+                // thread's columns ca .. and cb .., written and read by the same thread (coalesced 512 B per warp and word)
+                auto stash_at = [&](int slot, int t) { return my_stash + (size_t)((slot * 16 + t) * 4 + 2 * (grp & 1)) * 128; };
+                if (g == 3 || g == 4) {
+                    const float4* sp = stash_at(4 - g, tp);
+                    csa = ld_keep4(sp, stash_keep); csb = ld_keep4(sp + 128, stash_keep);
+                }
                 mbar_wait_warp(bar(C::kBarDFull), dphase, lane, pd);
                 dphase ^= 1u;
                 tc_fence_after();
-                uint32_t v[4];
-                TC_LD2(regD + lane_off + (uint32_t)fa, v[0], v[1]);
-                TC_LD2(regD + lane_off + (uint32_t)fb, v[2], v[3]);
-#pragma unroll 4
-                for (int t = 0; t < 16; ++t) {
+                const bool trace = dbg && blockIdx.x == 0 && it == 4 && warp == kFirstEpiWarp && lane == 0;
+                if (trace) dbg[160 + g] = (unsigned long long)clock64();            // accumulator of GEMM g seen complete
+                uint32_t v[8];
+                TC_LD4(regD + lane_off + 16u * (uint32_t)tp + (uint32_t)ca, v);
+                TC_LD4(regD + lane_off + 16u * (uint32_t)tp + (uint32_t)cb, (v + 4));
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int t = 2 * j + tp;
                     const uint32_t addr = regD + lane_off + 16u * (uint32_t)t;
                     tc_wait_ld();
-                    float cur[4];
+                    float cur[8];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) cur[i] = __uint_as_float(v[i]);    // features fa, fa + 1, fb, fb + 1
-                    if (t < 15) {   // prefetch the next slice's columns under the math
-                        TC_LD2(addr + 16u + (uint32_t)fa, v[0], v[1]);
-                        TC_LD2(addr + 16u + (uint32_t)fb, v[2], v[3]);
+                    for (int i = 0; i < 8; ++i) cur[i] = __uint_as_float(v[i]);    // features ca .. ca + 3, cb .. cb + 3
+                    if (j < 7) {   // prefetch this warp's next slice under the math
+                        TC_LD4(addr + 32u + (uint32_t)ca, v);
+                        TC_LD4(addr + 32u + (uint32_t)cb, (v + 4));
                     }
-                    // Front: what the next GEMM's operand needs.  The K-step is published one slice LATE (after the next slice's
+                    // Front: what the next GEMM's operand needs.  A K-step is published one iteration LATE (after the next slice's
                     // math, when its tensor-memory store has long completed: no stall on tcgen05.wait::st) -- except the first
                     // one of a GEMM, which is what the idle tensor pipe is waiting for.
-                    uint32_t o[4];
-                    float zz[4] = {0.f, 0.f, 0.f, 0.f};
-                    float2 wa0 = make_float2(0.f, 0.f), wa1 = wa0, wb0 = wa0, wb1 = wa0;
+                    uint32_t o[8];
+                    float zz[8];
+                    float2 w4a[4], w4b[4];
                     const bool stores = g < 5 || has_next;
                     if (g < 3) {
                         // forward: z = D / S + b'
-                        const float2 ba = *reinterpret_cast<const float2*>(s_bias + g * 256 + 16 * t + fa);
-                        const float2 bb = *reinterpret_cast<const float2*>(s_bias + g * 256 + 16 * t + fb);
-                        zz[0] = fmaf(cur[0], inv, ba.x); zz[1] = fmaf(cur[1], inv, ba.y);
-                        zz[2] = fmaf(cur[2], inv, bb.x); zz[3] = fmaf(cur[3], inv, bb.y);
+                        const float4 ba = *reinterpret_cast<const float4*>(s_bias + g * 256 + 16 * t + ca);
+                        const float4 bb = *reinterpret_cast<const float4*>(s_bias + g * 256 + 16 * t + cb);
+                        zz[0] = fmaf(cur[0], inv, ba.x); zz[1] = fmaf(cur[1], inv, ba.y); zz[2] = fmaf(cur[2], inv, ba.z); zz[3] = fmaf(cur[3], inv, ba.w);
+                        zz[4] = fmaf(cur[4], inv, bb.x); zz[5] = fmaf(cur[5], inv, bb.y); zz[6] = fmaf(cur[6], inv, bb.z); zz[7] = fmaf(cur[7], inv, bb.w);
                         if (g < 2) {
-                            split_pack<true>(sin_mufu(zz[0]), sin_mufu(zz[2]), o[0], o[2]);
-                            split_pack<true>(sin_mufu(zz[1]), sin_mufu(zz[3]), o[1], o[3]);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) split_pack<true>(sin_mufu(zz[i]), sin_mufu(zz[4 + i]), o[i], o[4 + i]);
                         } else {
                             // last hidden layer: start the backward sweep with G w4 (.) cos z3
-                            wa0 = s_w4[16 * t + fa]; wa1 = s_w4[16 * t + fa + 1]; wb0 = s_w4[16 * t + fb]; wb1 = s_w4[16 * t + fb + 1];
-                            split_pack<true>(cos_mufu(zz[0]) * wa0.y, cos_mufu(zz[2]) * wb0.y, o[0], o[2]);
-                            split_pack<true>(cos_mufu(zz[1]) * wa1.y, cos_mufu(zz[3]) * wb1.y, o[1], o[3]);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                w4a[i] = s_w4[16 * t + ca + i]; w4b[i] = s_w4[16 * t + cb + i];
+                                split_pack<true>(cos_mufu(zz[i]) * w4a[i].y, cos_mufu(zz[4 + i]) * w4b[i].y, o[i], o[4 + i]);
+                            }
                         }
                     } else if (g < 5) {
                         // backward through layer 6-g: g_{l-1} = (D / S) (.) cos z_{l-1}   (cosines from the stash)
-                        const float gg[4] = {cur[0] * inv * cs.x, cur[1] * inv * cs.y, cur[2] * inv * cs.z, cur[3] * inv * cs.w};
-                        if (t < 15) cs = ld_keep4(my_stash + (size_t)(((4 - g) * 16 + t + 1) * 4 + grp) * 128, stash_keep);
-                        split_pack<true>(gg[0], gg[2], o[0], o[2]);
-                        split_pack<true>(gg[1], gg[3], o[1], o[3]);
+                        const float gg[8] = {cur[0] * inv * csa.x, cur[1] * inv * csa.y, cur[2] * inv * csa.z, cur[3] * inv * csa.w,
+                                             cur[4] * inv * csb.x, cur[5] * inv * csb.y, cur[6] * inv * csb.z, cur[7] * inv * csb.w};
+                        if (j < 7) {
+                            const float4* sp = stash_at(4 - g, t + 2);
+                            csa = ld_keep4(sp, stash_keep); csb = ld_keep4(sp + 128, stash_keep);
+                        }
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) split_pack<true>(gg[i], gg[4 + i], o[i], o[4 + i]);
                     } else if (has_next) {
                         // these accumulator columns (region P, slice t) are dead now (cur holds them): the next tile's layer 0 goes there
                         layer0_cols(t, s_next[0], s_next[1], s_next[2], o);
                     }
                     if (stores) {
-                        if (t >= 2) publish_step(t - 1);
-                        TC_ST2(addr + (uint32_t)fa, o[0], o[1]);
-                        TC_ST2(addr + (uint32_t)fb, o[2], o[3]);
-                        if (t == 0) publish_step(0);
+                        if (j >= 2) publish_step(t - 2);
+                        TC_ST4(addr + (uint32_t)ca, o);
+                        TC_ST4(addr + (uint32_t)cb, (o + 4));
+                        if (j == 0) publish_step(t);
+                        if (trace) dbg[168 + g * 8 + j] = (unsigned long long)clock64();   // slice of iteration j stored (published one later)
                     }
                     // Back: everything else of the slice, off the hand-over path.
                     if (g < 2) {
-                        st_keep4(my_stash + (size_t)((g * 16 + t) * 4 + grp) * 128,
-                                 make_float4(cos_mufu(zz[0]), cos_mufu(zz[1]), cos_mufu(zz[2]), cos_mufu(zz[3])), stash_keep);
+                        float4* sp = stash_at(g, t);
+                        st_keep4(sp, make_float4(cos_mufu(zz[0]), cos_mufu(zz[1]), cos_mufu(zz[2]), cos_mufu(zz[3])), stash_keep);
+                        st_keep4(sp + 128, make_float4(cos_mufu(zz[4]), cos_mufu(zz[5]), cos_mufu(zz[6]), cos_mufu(zz[7])), stash_keep);
                     } else if (g == 2) {
-                        acc_y = fmaf(sin_mufu(zz[0]), wa0.x, acc_y);   // y += w4 . sin z3
-                        acc_y = fmaf(sin_mufu(zz[1]), wa1.x, acc_y);
-                        acc_y = fmaf(sin_mufu(zz[2]), wb0.x, acc_y);
-                        acc_y = fmaf(sin_mufu(zz[3]), wb1.x, acc_y);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {   // y += w4 . sin z3
+                            acc_y = fmaf(sin_mufu(zz[i]), w4a[i].x, acc_y);
+                            acc_y = fmaf(sin_mufu(zz[4 + i]), w4b[i].x, acc_y);
+                        }
                     } else if (g == 5) {
                         // input layer: g_0 = (D / S) (.) cos z_0 (recomputed), dy/dx += g_0 W0'
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const float4 w = s_w0[16 * t + (i < 2 ? fa + i : fb + i - 2)];
+                        for (int i = 0; i < 8; ++i) {
+                            const float4 w = s_w0[16 * t + (i < 4 ? ca + i : cb + i - 4)];
                             const float z0 = fmaf(w.z, pz, fmaf(w.y, py, fmaf(w.x, px, w.w)));
                             const float g0 = cur[i] * inv * cos_mufu(z0);
                             gx = fmaf(g0, w.x, gx);
@@ -923,7 +946,7 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
                         }
                     }
                 }
-                if (g < 5 || has_next) publish_step(15);
+                if (g < 5 || has_next) publish_step(14 + tp);
             }
 
             // ---- outputs: sum the four feature-quarter partials of every point in a fixed order -------------------
@@ -971,7 +994,7 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
             }
         }
         }
-        if (dbg && blockIdx.x == 0 && lane == 0) dbg[8 + warp] = wait_d;
+        if (dbg && blockIdx.x == 0 && lane == 0) dbg[8 + warp - kFirstEpiWarp] = wait_d;
     }
 
     // ---- teardown ----------------------------------------------------------------------------------------------------
@@ -1071,7 +1094,7 @@ __global__ void mlp_pack_out_kernel(const float* __restrict__ W2, const float* _
 template <int CTAS, int KIND>
 int launch_rev(const void* packed, const SirenHeader& h, const float* x, int64_t n, float* y, float* J, float* H, void* ws,
                cudaStream_t stream, const RowPeers peers = RowPeers{}) {
-    using C = RevCfg<CTAS>;
+    using C = RevCfg<CTAS, KIND>;
     auto kern = siren_rev_kernel<CTAS, KIND>;
     const int smem = (int)(KIND == 2 ? C::kSmemTotalMlp : C::kSmemTotal) + 1024;
     INF3DP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -1083,8 +1106,8 @@ int launch_rev(const void* packed, const SirenHeader& h, const float* x, int64_t
     static const bool debug = getenv("INF3DP_TC_DEBUG") != nullptr;
     unsigned long long* dbg = nullptr;
     if (debug) {
-        INF3DP_CUDA(cudaMalloc(&dbg, 64 * sizeof(unsigned long long)));
-        INF3DP_CUDA(cudaMemsetAsync(dbg, 0, 64 * sizeof(unsigned long long), stream));
+        INF3DP_CUDA(cudaMalloc(&dbg, 256 * sizeof(unsigned long long)));
+        INF3DP_CUDA(cudaMemsetAsync(dbg, 0, 256 * sizeof(unsigned long long), stream));
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
@@ -1101,11 +1124,21 @@ int launch_rev(const void* packed, const SirenHeader& h, const float* x, int64_t
     INF3DP_CUDA(cudaLaunchKernelEx(&cfg, kern, (const char*)packed, h, x, n, y, J, H, (float4*)ws, dbg, peers));
     INF3DP_LAUNCH_CHECK("siren_rev_kernel");
     if (debug) {
-        unsigned long long hbuf[64];
+        unsigned long long hbuf[256];
         INF3DP_CUDA(cudaMemcpyAsync(hbuf, dbg, sizeof(hbuf), cudaMemcpyDeviceToHost, stream));
         INF3DP_CUDA(cudaStreamSynchronize(stream));
         INF3DP_CUDA(cudaFree(dbg));
         const double u = hbuf[3] ? (double)hbuf[3] : 1.0;
+        if (KIND == 0 && hbuf[64] != 0) {   // timeline of unit 4 of block 0 (cycles since its first MMA): MMA issue per K-step, epilogue warp 0
+            const unsigned long long t0 = hbuf[64];
+            for (int g = 0; g < 6; ++g) {
+                fprintf(stderr, "[inf3dp rev trace] GEMM %d K-step issued at:", g);
+                for (int t = 0; t < 16; ++t) fprintf(stderr, " %lld", (long long)(hbuf[64 + g * 16 + t] - t0));
+                fprintf(stderr, "\n[inf3dp rev trace] GEMM %d accumulator seen by warp 0 at %lld, its slices stored at:", g, (long long)(hbuf[160 + g] - t0));
+                for (int j = 0; j < 8; ++j) fprintf(stderr, " %lld", (long long)(hbuf[168 + g * 8 + j] - t0));
+                fprintf(stderr, "\n");
+            }
+        }
         for (int g = 0; g < 6; ++g)
             fprintf(stderr, "[inf3dp rev debug] GEMM %d: a_ready wait per round %.0f %.0f %.0f %.0f cyc\n", g, hbuf[32 + g * 4] / u,
                     hbuf[33 + g * 4] / u, hbuf[34 + g * 4] / u, hbuf[35 + g * 4] / u);

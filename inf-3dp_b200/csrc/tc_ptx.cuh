@@ -130,6 +130,12 @@ __host__ __device__ constexpr uint32_t make_idesc(int n) {
                    "=r"(v[15])                                                                                   \
                  : "r"(addr) : "memory")
 
+#define TC_LD4(addr, v)                                                                                           \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"                                       \
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(addr) : "memory")
+#define TC_ST4(addr, v)                                                                                           \
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};"                                       \
+                 ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory")
 #define TC_LD2(addr, v0, v1)                                                                                      \
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(v0), "=r"(v1) : "r"(addr) : "memory")
 #define TC_ST2(addr, v0, v1)                                                                                      \
@@ -216,6 +222,28 @@ __device__ __forceinline__ void mma_ts_pair(uint32_t d_tmem, uint32_t a_tmem, ui
     asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
                  "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n}"
                  ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+// The same instructions issued from CONVERGENT warp code by one elected lane (elect.sync inside the asm): the compiler keeps
+// the operands on the uniform datapath and emits ELECT + one predicated UTCHMMA, instead of the per-active-thread loop it wraps
+// around a uniform-datapath instruction that sits in a divergent `if (lane == 0)` region (5 more instructions per MMA).
+__device__ __forceinline__ void mma_ts_pair_elect(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n.reg .pred p, q;\nelect.sync _|q, 0xffffffff;\nsetp.ne.b32 p, %4, 0;\n"
+                 "@q tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n}"
+                 ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void mma_ts_elect(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n.reg .pred p, q;\nelect.sync _|q, 0xffffffff;\nsetp.ne.b32 p, %4, 0;\n"
+                 "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}"
+                 ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair_elect(uint32_t bar, uint16_t cta_mask) {
+    asm volatile("{\n.reg .pred q;\nelect.sync _|q, 0xffffffff;\n"
+                 "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n}"
+                 ::"r"(bar), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ void tc_commit_elect(uint32_t bar) {
+    asm volatile("{\n.reg .pred q;\nelect.sync _|q, 0xffffffff;\n"
+                 "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}" ::"r"(bar) : "memory");
 }
 __host__ __device__ constexpr uint32_t make_idesc_mn(int m, int n) {
     return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
