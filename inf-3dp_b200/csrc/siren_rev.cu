@@ -916,11 +916,11 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
                         layer0_cols(t, s_next[0], s_next[1], s_next[2], o);
                     }
                     if (stores) {
-                        if (j >= 2) publish_step(t - 2);
                         TC_ST4(addr + (uint32_t)ca, o);
                         TC_ST4(addr + (uint32_t)cb, (o + 4));
-                        if (j == 0) publish_step(t);
+                        publish_step(t);
                         if (trace) dbg[168 + g * 8 + j] = (unsigned long long)clock64();   // slice of iteration j stored (published one later)
+                        if (dbg && blockIdx.x == 0 && it == 4 && g == 2 && j == 0 && lane == 0) dbg[216 + warp] = (unsigned long long)clock64();
                     }
                     // Back: everything else of the slice, off the hand-over path.
                     if (g < 2) {
@@ -946,7 +946,6 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
                         }
                     }
                 }
-                if (g < 5 || has_next) publish_step(14 + tp);
             }
 
             // ---- outputs: sum the four feature-quarter partials of every point in a fixed order -------------------
@@ -1138,6 +1137,9 @@ int launch_rev(const void* packed, const SirenHeader& h, const float* x, int64_t
                 for (int j = 0; j < 8; ++j) fprintf(stderr, " %lld", (long long)(hbuf[168 + g * 8 + j] - t0));
                 fprintf(stderr, "\n");
             }
+            fprintf(stderr, "[inf3dp rev trace] GEMM 2: first slice stored + published by warps 0..15 at:");
+            for (int w = 0; w < 16; ++w) fprintf(stderr, " %lld", (long long)(hbuf[216 + w] - t0));
+            fprintf(stderr, "\n");
         }
         for (int g = 0; g < 6; ++g)
             fprintf(stderr, "[inf3dp rev debug] GEMM %d: a_ready wait per round %.0f %.0f %.0f %.0f cyc\n", g, hbuf[32 + g * 4] / u,
