@@ -155,8 +155,8 @@ siren_tc_kernel(const char* __restrict__ packed, SirenHeader h, const float* __r
             }
         }
     } else if (warp == kMmaWarp) {
-        // ================= MMA issuer ===========================================================================
-        if (lane == 0) {
+        // ================= MMA issuer: the whole warp runs the loop convergently, one elected lane issues (tc_ptx.cuh) ==========
+        {
             constexpr uint32_t idesc256 = make_idesc(256);
             uint32_t stage = 0, wphase = 0;
             uint32_t aphase = 0;  // parity of the a_ready barriers (one completion per activation version)
@@ -182,17 +182,17 @@ siren_tc_kernel(const char* __restrict__ packed, SirenHeader h, const float* __r
                             const uint32_t sb = ring + (uint32_t)(tt >> 1) * 32768u + (uint32_t)(tt & 1) * 8192u;
                             const uint64_t bh = make_desc(sb, 4096, 128);
                             const uint32_t a_hi = regA + 16u * (uint32_t)t;
-                            mma_ts(regD, a_hi, bh, idesc256, t > 0 ? 1u : 0u);
+                            mma_ts_elect(regD, a_hi, bh, idesc256, t > 0 ? 1u : 0u);
                             if (PRECISE) {
                                 const uint64_t bl = make_desc(sb + 16384u, 4096, 128);
-                                mma_ts(regD, a_hi + 8u, bh, idesc256, 1u);
-                                mma_ts(regD, a_hi, bl, idesc256, 1u);
+                                mma_ts_elect(regD, a_hi + 8u, bh, idesc256, 1u);
+                                mma_ts_elect(regD, a_hi, bl, idesc256, 1u);
                             }
                         }
-                        tc_commit(bar(kBarWEmpty + stage));  // stage free once these MMAs have read it
+                        tc_commit_elect(bar(kBarWEmpty + stage));  // stage free once these MMAs have read it
                         if (++stage == kStages) { stage = 0; wphase ^= 1u; }
                     }
-                    tc_commit(bar(kBarDFull));
+                    tc_commit_elect(bar(kBarDFull));
                     if (dbg) {  // instrumentation only: how long after the last issue does D become visible?
                         const long long t0 = clock64();
                         mbar_wait(bar(kBarDFull), dbg_dphase);
@@ -203,7 +203,7 @@ siren_tc_kernel(const char* __restrict__ packed, SirenHeader h, const float* __r
                 }
                 // (the linear output layer is folded into the last hidden layer's epilogue on the CUDA cores)
             }
-            if (dbg && blockIdx.x == 0) {
+            if (dbg && blockIdx.x == 0 && lane == 0) {
                 dbg[4] = dbg_lag;
                 dbg[0] = (unsigned long long)(clock64() - t_begin);
                 dbg[1] = wait_a;
