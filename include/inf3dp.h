@@ -36,9 +36,10 @@ enum {
     INF3DP_MODE_SIMT = 1,       /* FP32 CUDA-core kernel: any supported configuration, orders 0..2     */
     INF3DP_MODE_TC_PRECISE = 2, /* tcgen05 tensor cores, FP16 hi/lo split operands (3 MMAs), FP32 acc. */
     INF3DP_MODE_TC_FAST = 3,    /* tcgen05 tensor cores, single FP16 operands (does NOT meet 0.1 deg)  */
-    INF3DP_MODE_TC_REVERSE = 4  /* tcgen05 CTA pairs, reverse-mode value+gradient (out == 1, order == 1) or
-                                   forward-over-reverse value+gradient+Hessian (out == 1, order == 2), FP16
-                                   hi/lo split operands; needs the workspace of inf3dp_siren_jet_ws         */
+    INF3DP_MODE_TC_REVERSE = 4  /* tcgen05 CTA pairs, single-output sine networks, FP16 hi/lo split operands: the
+                                   forward sweep alone (order 0), reverse-mode value+gradient (order 1) or
+                                   forward-over-reverse value+gradient+Hessian (order 2); orders 1 and 2 need the
+                                   workspace of inf3dp_siren_jet_ws                                           */
 };
 
 const char* inf3dp_last_error(void);
@@ -87,7 +88,8 @@ int inf3dp_siren_jet(const void* packed, const float* x, int64_t n, int order, f
  * tile (256 KB per SM) between the sweeps.  Order-2 queries of such networks (diff_operators.py:6-44 hessian / hessian3d)
  * then run forward-over-reverse on the same engine -- the point and its three tangents d/dx_i through the same forward +
  * backward sweep, 32 points per tile, Hessian rows symmetrised -- instead of the 10-row second-order forward jet that
- * INF3DP_MODE_TC_PRECISE (and AUTO without a workspace) selects. */
+ * INF3DP_MODE_TC_PRECISE (and AUTO without a workspace) selects.  Order-0 queries of such networks run the forward sweep of
+ * the same engine (no workspace needed); the value is bit-identical to the one an order-1 query returns. */
 size_t inf3dp_siren_jet_workspace_bytes(void);
 /* Process-wide cap on the SMs the persistent SIREN engines occupy (0 = all, the default).  A multi-GPU caller that overlaps
  * the all-gather of chunk i with the query of chunk i+1 leaves a few SMs to the NCCL kernels (inf3dp/dist.py). */

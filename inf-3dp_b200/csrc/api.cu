@@ -285,6 +285,7 @@ int inf3dp_siren_jet_ws(const void* packed, const float* x, int64_t n, int order
             if (jet2_capable && have_ws) return siren_hess_launch(packed, h, x, n, y, J, H, workspace, workspace_bytes, st);
             if (jet2_capable) return siren_jet2_launch(packed, h, x, n, y, J, H, st);
             if (mlp_capable) return siren_mlp_launch(packed, h, x, n, y, st);
+            if (h.rev_ok && order == 0) return siren_value_launch(packed, h, x, n, y, st);   // single-output sine field: CTA-pair engine
             if (tc_capable) return siren_tc_launch(packed, h, x, n, order, y, J, true, st);
             return siren_simt_launch(packed, h, x, n, order, y, J, H, st);
         case INF3DP_MODE_SIMT:
@@ -298,9 +299,10 @@ int inf3dp_siren_jet_ws(const void* packed, const float* x, int64_t n, int order
                              "out<=4 and order<=1");
             return siren_tc_launch(packed, h, x, n, order, y, J, mode == INF3DP_MODE_TC_PRECISE, st);
         case INF3DP_MODE_TC_REVERSE:
+            if (h.rev_ok && order == 0) return siren_value_launch(packed, h, x, n, y, st);
             if (jet2_capable) return siren_hess_launch(packed, h, x, n, y, J, H, workspace, workspace_bytes, st);
-            INF3DP_CHECK_ARG(rev_capable, "siren_jet: reverse-mode engine needs sine, in=3, hidden=256, 3 hidden layers, "
-                             "out=1 and order 1 or 2");
+            INF3DP_CHECK_ARG(rev_capable, "siren_jet: the CTA-pair engine needs sine, in=3, hidden=256, 3 hidden layers, "
+                             "out=1");
             return siren_rev_launch(packed, h, x, n, y, J, workspace, workspace_bytes, st);
         default:
             set_error("siren_jet: unknown mode %d", mode);

@@ -152,6 +152,7 @@ int siren_mlp_pack(const float* const* W, const float* const* b, int out_feature
 int siren_mlp_launch(const void* packed, const SirenHeader& h, const float* x, int64_t n, float* y, cudaStream_t stream);
 int siren_jet2_launch(const void* packed, const SirenHeader& h, const float* x, int64_t n, float* y, float* J, float* H,
                       cudaStream_t stream);
+int siren_value_launch(const void* packed, const SirenHeader& h, const float* x, int64_t n, float* y, cudaStream_t stream);
 int siren_hess_launch(const void* packed, const SirenHeader& h, const float* x, int64_t n, float* y, float* J, float* H,
                       void* ws, size_t ws_bytes, cudaStream_t stream);
 

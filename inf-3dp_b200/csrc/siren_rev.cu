@@ -105,6 +105,9 @@ struct RevCfg {
 //         tensor memory: c = 0 the primal row (a_l, then G g_l), c = 1..3 the tangent rows (da_l/dx_i, then kT G dg_l/dx_i).
 //         The primal row yields (y, dy/dx), tangent row i yields row i of the Hessian.  24 row-GEMMs per point instead of the
 //         30 of the second-order jet, and about half of its epilogue instructions per point.
+// KIND 4: value only (order 0) of the same networks -- the forward sweep of KIND 0 alone: 3 GEMMs per tile of 128 points, no
+//         cosines, no scratch, the column-split epilogue; the unit boundary is fused as in KIND 1 (odd number of GEMMs per unit:
+//         the two halves of tensor memory swap roles from unit to unit).
 // Destinations of the packed (value, grad) rows when the query is fused with the multi-GPU all-gather (KIND 0 only):
 // either one NVLink multicast address (multimem.st, replicated by the switch) or up to 8 peer-mapped buffers.
 constexpr int kMaxRowPeers = 8;
@@ -120,12 +123,12 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
                  float* __restrict__ y, float* __restrict__ J, float* __restrict__ Hout, float4* __restrict__ stash,
                  unsigned long long* __restrict__ dbg, const RowPeers peers) {
     using C = RevCfg<CTAS, KIND>;
-    constexpr int kGemms = (KIND == 0 || KIND == 3) ? 6 : (KIND == 1 ? 3 : 1);
+    constexpr int kGemms = (KIND == 0 || KIND == 3) ? 6 : ((KIND == 1 || KIND == 4) ? 3 : 1);
     constexpr int kTilePts = KIND == 1 ? 12 : (KIND == 3 ? 32 : 128);
     constexpr size_t kImgBase = KIND == 2 ? kMlpOffImg : kRevOffImg;
-    // KIND 0: column-split epilogue -- the four warps of a tensor-memory quadrant share every 16-feature slice (four accumulator
+    // KIND 0, 4: column-split epilogue -- the four warps of a tensor-memory quadrant share every 16-feature slice (four accumulator
     // columns each) and publish it K-step by K-step, instead of owning four whole slices each and publishing rounds of four
-    constexpr bool kFine = KIND == 0;
+    constexpr bool kFine = KIND == 0 || KIND == 4;
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t sbase = (smem_u32(smem_dyn) + 1023u) & ~1023u;   // same offset in both CTAs of a pair
     unsigned char* sptr = smem_dyn + (sbase - smem_u32(smem_dyn));
@@ -236,7 +239,7 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
                 for (int g = 0; g < kGemms; ++g) {
                     // KIND 1 runs an odd number of GEMMs per unit and fuses the unit boundary: the two halves of tensor memory swap
                     // roles from unit to unit (the next tile's layer 0 overwrites the accumulator slices of GEMM 2 as they are read)
-                    const int par = (g + (KIND == 1 ? it : 0)) & 1;
+                    const int par = (g + ((KIND == 1 || KIND == 4) ? it : 0)) & 1;
                     const uint32_t regA = par ? regionQ : regionP;
                     const uint32_t regD = par ? regionP : regionQ;
 #pragma unroll
@@ -557,6 +560,116 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
             // s_part is rewritten only after three more d_full phases, which every epilogue warp (the readers above included)
             // has to pass first
             pt = npt; pvalid = nvalid; px = nx; py = ny; pz = nz;
+        }
+        } else if constexpr (KIND == 4) {
+        // ---------------- value only: the forward sweep with the column-split epilogue of KIND 0 ---------------------------------
+        const int ca = 4 * (grp & 1), cb = 8 + ca, tp = grp >> 1;   // this warp's columns ca .., cb .. of the slices t = 2 j + tp
+        auto load_point = [&](int it, int64_t& pt, bool& pvalid, float& px, float& py, float& pz) {
+            const int64_t tile = (unit0 + (int64_t)it * unit_stride) * CTAS + rank;
+            pt = tile * 128 + row;
+            pvalid = it < my_units && pt < n;
+            px = py = pz = 0.f;
+            if (pvalid) { px = x[3 * pt]; py = x[3 * pt + 1]; pz = x[3 * pt + 2]; }
+        };
+        auto layer0_cols = [&](int t, float qx, float qy, float qz, uint32_t* o) {   // a0 = sin(W0' x + b0'), FP32
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float r2[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const float4 w = s_w0[16 * t + (u ? cb : ca) + i];
+                    r2[u] = sin_layer0(fmaf(w.z, qz, fmaf(w.y, qy, fmaf(w.x, qx, w.w))));
+                }
+                split_pack<true>(r2[0], r2[1], o[i], o[4 + i]);
+            }
+        };
+        int64_t pt;
+        bool pvalid;
+        float px, py, pz;
+        load_point(0, pt, pvalid, px, py, pz);
+        if (my_units > 0) {
+#pragma unroll 1
+            for (int j = 0; j < 8; ++j) {
+                const int t = 2 * j + tp;
+                uint32_t o[8];
+                layer0_cols(t, px, py, pz, o);
+                const uint32_t addr = regionP + lane_off + 16u * (uint32_t)t;
+                TC_ST4(addr + (uint32_t)ca, o);
+                TC_ST4(addr + (uint32_t)cb, (o + 4));
+                publish_step(t);
+            }
+        }
+        for (int it = 0; it < my_units; ++it) {
+            float* s_next = reinterpret_cast<float*>(sptr + C::kSmemNext) + 3 * (grp * 128 + row);
+            const bool has_next = it + 1 < my_units;
+            float acc_y = 0.f;
+#pragma unroll
+            for (int g = 0; g < 3; ++g) {
+                const uint32_t regD = ((g + it) & 1) ? regionP : regionQ;
+                const float inv = s_misc[g];
+                if (g == 0) {   // the next tile's point: consumed two GEMMs later
+                    int64_t npt; bool nvalid; float nx, ny, nz;
+                    load_point(it + 1, npt, nvalid, nx, ny, nz);
+                    s_next[0] = nx; s_next[1] = ny; s_next[2] = nz;
+                }
+                mbar_wait_warp(bar(C::kBarDFull), dphase, lane, pd);
+                dphase ^= 1u;
+                tc_fence_after();
+                uint32_t v[8];
+                TC_LD4(regD + lane_off + 16u * (uint32_t)tp + (uint32_t)ca, v);
+                TC_LD4(regD + lane_off + 16u * (uint32_t)tp + (uint32_t)cb, (v + 4));
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int t = 2 * j + tp;
+                    const uint32_t addr = regD + lane_off + 16u * (uint32_t)t;
+                    tc_wait_ld();
+                    float cur[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) cur[i] = __uint_as_float(v[i]);
+                    if (j < 7) {
+                        TC_LD4(addr + 32u + (uint32_t)ca, v);
+                        TC_LD4(addr + 32u + (uint32_t)cb, (v + 4));
+                    }
+                    const float4 ba = *reinterpret_cast<const float4*>(s_bias + g * 256 + 16 * t + ca);
+                    const float4 bb = *reinterpret_cast<const float4*>(s_bias + g * 256 + 16 * t + cb);
+                    const float zz[8] = {fmaf(cur[0], inv, ba.x), fmaf(cur[1], inv, ba.y), fmaf(cur[2], inv, ba.z), fmaf(cur[3], inv, ba.w),
+                                         fmaf(cur[4], inv, bb.x), fmaf(cur[5], inv, bb.y), fmaf(cur[6], inv, bb.z), fmaf(cur[7], inv, bb.w)};
+                    uint32_t o[8];
+                    if (g < 2) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) split_pack<true>(sin_mufu(zz[i]), sin_mufu(zz[4 + i]), o[i], o[4 + i]);
+                        TC_ST4(addr + (uint32_t)ca, o);
+                        TC_ST4(addr + (uint32_t)cb, (o + 4));
+                        publish_step(t);
+                    } else {
+                        // these accumulator columns are dead now: the next tile's layer 0 goes there first, the value is summed behind it
+                        if (has_next) {
+                            layer0_cols(t, s_next[0], s_next[1], s_next[2], o);
+                            TC_ST4(addr + (uint32_t)ca, o);
+                            TC_ST4(addr + (uint32_t)cb, (o + 4));
+                            publish_step(t);
+                        }
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {   // y += w4 . sin z3
+                            acc_y = fmaf(sin_mufu(zz[i]), s_w4[16 * t + ca + i].x, acc_y);
+                            acc_y = fmaf(sin_mufu(zz[4 + i]), s_w4[16 * t + cb + i].x, acc_y);
+                        }
+                    }
+                }
+            }
+            // ---- output: sum the four partials of every point in a fixed order ---------------------------------------------
+            s_part[grp * 128 + row] = acc_y;
+            asm volatile("bar.sync 1, 512;" ::: "memory");
+            if (grp == 0 && pvalid)
+                y[pt] = (((s_part[row] + s_part[128 + row]) + s_part[256 + row]) + s_part[384 + row]) + s_misc[3];
+            // s_part is rewritten only after three more d_full phases, which every epilogue warp (the readers above included)
+            // has to pass first
+            {
+                const int64_t tile = (unit0 + (int64_t)(it + 1) * unit_stride) * CTAS + rank;
+                pt = tile * 128 + row;
+                pvalid = has_next && pt < n;
+                if (has_next) { px = s_next[0]; py = s_next[1]; pz = s_next[2]; }
+            }
         }
         } else if constexpr (KIND == 3) {
         // ---------------- forward-over-reverse: 32 points x (primal row + three tangent rows) ------------------------------
@@ -1146,7 +1259,7 @@ int launch_rev(const void* packed, const SirenHeader& h, const float* x, int64_t
                     hbuf[33 + g * 4] / u, hbuf[34 + g * 4] / u, hbuf[35 + g * 4] / u);
         fprintf(stderr, "[inf3dp rev debug] CTAS=%d KIND=%d block0: %.0f units, %.0f cyc/unit (%d GEMMs); MMA thread blocked on a_ready %.0f, "
                         "on w_full %.0f cyc/unit; epilogue warp0 blocked on d_full %.0f, warp5 %.0f, warp15 %.0f cyc/unit\n",
-                CTAS, KIND, u, hbuf[0] / u, (KIND == 0 || KIND == 3) ? 6 : (KIND == 1 ? 3 : 1), hbuf[1] / u, hbuf[2] / u, hbuf[8] / u, hbuf[13] / u, hbuf[23] / u);
+                CTAS, KIND, u, hbuf[0] / u, (KIND == 0 || KIND == 3) ? 6 : ((KIND == 1 || KIND == 4) ? 3 : 1), hbuf[1] / u, hbuf[2] / u, hbuf[8] / u, hbuf[13] / u, hbuf[23] / u);
     }
     return INF3DP_OK;
 }
@@ -1256,6 +1369,12 @@ int siren_jet2_launch(const void* packed, const SirenHeader& h, const float* x, 
     static const int ctas = [] { const char* e = getenv("INF3DP_REV_CTAS"); return e && atoi(e) == 1 ? 1 : 2; }();
     return ctas == 1 ? launch_rev<1, 1>(packed, h, x, n, y, J, H, nullptr, stream)
                      : launch_rev<2, 1>(packed, h, x, n, y, J, H, nullptr, stream);
+}
+
+// Value only (order 0) of single-output field networks on the CTA-pair engine (KIND 4).
+int siren_value_launch(const void* packed, const SirenHeader& h, const float* x, int64_t n, float* y, cudaStream_t stream) {
+    INF3DP_CHECK_ARG(h.rev_ok && h.off_rev != 0, "siren_value: packed weights carry no CTA-pair operand images");
+    return launch_rev<2, 4>(packed, h, x, n, y, nullptr, nullptr, nullptr, stream);
 }
 
 // The same outputs by forward-over-reverse differentiation (KIND 3): needs the reverse engine's scratch.

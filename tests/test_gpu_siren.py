@@ -338,6 +338,33 @@ def test_order2_forward_over_reverse_needs_the_workspace(golden):
     assert torch.equal(H, Hj)
 
 
+@pytest.mark.parametrize("n", [1, 127, 128, 129, 255, 256, 257, 1000, 100003])
+def test_value_only_on_the_cta_pair_engine(golden, n):
+    """Order-0 queries of single-output sine fields run the forward sweep of the reverse engine alone (modules.py:143-160;
+    what utils.field_querying and the SDF sweep of the collision query ask for): ragged sizes against the fp64 oracle and the
+    golden values, bit-identical to the value an order-1 query returns, batch-split invariant; tc_reverse selects it too."""
+    net = _net(golden)
+    g = torch.Generator().manual_seed(500 + n)
+    x = (torch.rand(n, 3, generator=g) * 2 - 1).cuda()
+    y, J, H = net.query(x, order=0)
+    assert y.shape == (n, 1) and J is None and H is None and torch.isfinite(y).all()
+    y1, _, _ = net.query(x, order=1)
+    assert torch.equal(y, y1)
+    yr, _, _ = net.query(x, order=0, mode="tc_reverse")
+    assert torch.equal(y, yr)
+    m = min(n, 4096)
+    yo, _, _ = so.siren_jet(layers_from_golden(golden, "sdf"), x[:m].cpu().numpy().astype(np.float64), order=0)
+    assert np.abs(y[:m].cpu().numpy() - yo).max() <= 2e-6
+    yt, _, _ = net.query(x, order=0, mode="tc_precise")
+    assert float((y - yt).abs().max()) <= 1e-6
+    if n > 40:
+        y2, _, _ = net.query(x[17:], order=0)
+        assert torch.equal(y2, y[17:])
+    xg = torch.from_numpy(golden["x"]).cuda()
+    yg, _, _ = net.query(xg, order=0)
+    assert np.abs(yg.cpu().numpy() - golden["sdf/y"]).max() <= TOL_F
+
+
 @pytest.mark.parametrize("gain", [1.0, 3.0, 8.0])
 def test_reverse_engine_range_scale_with_large_weights(golden, gain):
     """Hidden weights scaled up (a stand-in for trained fields with high-frequency content; pre-activations reach
