@@ -239,7 +239,7 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
                 for (int g = 0; g < kGemms; ++g) {
                     // KIND 1 runs an odd number of GEMMs per unit and fuses the unit boundary: the two halves of tensor memory swap
                     // roles from unit to unit (the next tile's layer 0 overwrites the accumulator slices of GEMM 2 as they are read)
-                    const int par = (g + ((KIND == 1 || KIND == 4) ? it : 0)) & 1;
+                    const int par = (g + ((KIND == 1 || KIND == 2 || KIND == 4) ? it : 0)) & 1;
                     const uint32_t regA = par ? regionQ : regionP;
                     const uint32_t regD = par ? regionP : regionQ;
 #pragma unroll
@@ -351,33 +351,53 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
         const float4* s_w2 = reinterpret_cast<const float4*>(sptr + C::kSmemMlpW2);   // [256][4 float4] = W2^T rows of 16
         float* s_lpart = reinterpret_cast<float*>(sptr + C::kSmemMlpPart);            // [4][16][128]
         const int out_f = h.out_features;
-        for (int it = 0; it < my_units; ++it) {
+        // The unit boundary is fused as in the field engines: the first tile's layer 0 is a prologue; every later tile's layer 0 is
+        // produced inside the rounds of the previous tile's epilogue, slice by slice over the accumulator columns that were just
+        // read (one GEMM per unit: the two halves of tensor memory swap roles from unit to unit), so the GEMM of tile i + 1 runs
+        // under the output layer of tile i instead of after it.
+        auto load_x = [&](int it, int64_t& pt, bool& pvalid, float4& xin) {
             const int64_t tile = (unit0 + (int64_t)it * unit_stride) * CTAS + rank;
-            const int64_t pt = tile * 128 + row;
-            const bool pvalid = pt < n;
-            float4 xin = make_float4(0.f, 0.f, 0.f, 0.f);
+            pt = tile * 128 + row;
+            pvalid = it < my_units && pt < n;
+            xin = make_float4(0.f, 0.f, 0.f, 0.f);
             if (pvalid) xin = reinterpret_cast<const float4*>(x)[pt];
-            // layer 0 (FP32): a0 = relu(W0 x + b0)
+        };
+        auto layer0_slice = [&](int m, const float4 xin, uint32_t* o) {   // a0 = relu(W0 x + b0), FP32
+#pragma unroll
+            for (int i = 0; i < 16; i += 2) {
+                float r2[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int f = 16 * m + (i >> 1) + 8 * u;   // K-slot pair (i, i + 1) holds features (i / 2, 8 + i / 2)
+                    const float4 w = s_w0[f];
+                    // x W^T + b in the accumulation order of a row-major dot product (k = 0..3), then the bias
+                    const float z = fmaf(w.w, xin.w, fmaf(w.z, xin.z, fmaf(w.y, xin.y, w.x * xin.x))) + s_bias[f];
+                    r2[u] = fmaxf(z, 0.f);
+                }
+                split_pack<true>(r2[0], r2[1], o[i >> 1], o[8 + (i >> 1)]);
+            }
+        };
+        int64_t pt;
+        bool pvalid;
+        float4 xin;
+        load_x(0, pt, pvalid, xin);
+        if (my_units > 0) {
 #pragma unroll 1
             for (int mi = 0; mi < 4; ++mi) {
                 const int m = grp + 4 * mi;
                 uint32_t o[16];
-#pragma unroll
-                for (int i = 0; i < 16; i += 2) {
-                    float r2[2];
-#pragma unroll
-                    for (int u = 0; u < 2; ++u) {
-                        const int f = 16 * m + (i >> 1) + 8 * u;   // K-slot pair (i, i + 1) holds features (i / 2, 8 + i / 2)
-                        const float4 w = s_w0[f];
-                        // x W^T + b in the accumulation order of a row-major dot product (k = 0..3), then the bias
-                        const float z = fmaf(w.w, xin.w, fmaf(w.z, xin.z, fmaf(w.y, xin.y, w.x * xin.x))) + s_bias[f];
-                        r2[u] = fmaxf(z, 0.f);
-                    }
-                    split_pack<true>(r2[0], r2[1], o[i >> 1], o[8 + (i >> 1)]);
-                }
+                layer0_slice(m, xin, o);
                 TC_ST16(regionP + lane_off + 16u * (uint32_t)m, o);
                 publish(mi);
             }
+        }
+        for (int it = 0; it < my_units; ++it) {
+            const bool has_next = it + 1 < my_units;
+            const uint32_t regD = (it & 1) ? regionP : regionQ;
+            int64_t npt;
+            bool nvalid;
+            float4 xnext;
+            load_x(it + 1, npt, nvalid, xnext);   // latency hidden behind this tile's GEMM
             float acc[kMlpMaxOut];
 #pragma unroll
             for (int o = 0; o < kMlpMaxOut; ++o) acc[o] = 0.f;
@@ -387,15 +407,22 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
                 dphase ^= 1u;
                 tc_fence_after();
                 uint32_t v[16];
-                TC_LD16(regionQ + lane_off + 16u * (uint32_t)grp, v);
+                TC_LD16(regD + lane_off + 16u * (uint32_t)grp, v);
 #pragma unroll 1
                 for (int mi = 0; mi < 4; ++mi) {
                     const int m = grp + 4 * mi;
+                    const uint32_t addr = regD + lane_off + 16u * (uint32_t)m;
                     tc_wait_ld();
                     float cur[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) cur[i] = __uint_as_float(v[i]);
-                    if (mi < 3) TC_LD16(regionQ + lane_off + 16u * (uint32_t)(m + 4), v);
+                    if (mi < 3) TC_LD16(addr + 64u, v);
+                    if (has_next) {   // these accumulator columns are dead now: the next tile's layer 0 goes there first
+                        uint32_t o[16];
+                        layer0_slice(m, xnext, o);
+                        TC_ST16(addr, o);
+                        publish(mi);
+                    }
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         const int f = 16 * m + i;
@@ -426,6 +453,7 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
                 }
             }
             asm volatile("bar.sync 1, 512;" ::: "memory");   // the partials are rewritten by the next tile's epilogue
+            pt = npt; pvalid = nvalid; xin = xnext;
         }
         } else if constexpr (KIND == 1) {
         // ---------------- second-order forward jet: 3 points x 10 rows per quadrant ------------------------------------------
