@@ -255,6 +255,9 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
                         }
                         tc_fence_after();
                         const uint32_t ring = sbase + C::kSmemRing + stage * C::kStageBytes;
+                        // descriptor of the stage's first K-step; the others differ in the 14-bit start-address field only (shared
+                        // memory addresses stay below 2^18, so adding (byte offset >> 4) never carries out of the field)
+                        const uint64_t desc0 = make_desc(ring, 2048, 128);
 #pragma unroll
                         for (int tt = 0; tt < kStageK; ++tt) {
                             const int t = kStageK * r + tt;
@@ -271,8 +274,7 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
                             const uint32_t a_hi = regA + 16u * (uint32_t)t;
                             const uint32_t acc = t > 0 ? 1u : 0u;
                             if (CTAS == 2) {
-                                const uint32_t sb = ring + (uint32_t)tt * (uint32_t)kPerKBytes;
-                                const uint64_t bh = make_desc(sb, 2048, 128), bl = make_desc(sb + 4096u, 2048, 128);
+                                const uint64_t bh = desc0 + (uint64_t)((uint32_t)tt * (uint32_t)(kPerKBytes >> 4)), bl = bh + (uint64_t)(4096u >> 4);
                                 mma_ts_pair_elect(regD, a_hi, bh, idesc, acc);
                                 mma_ts_pair_elect(regD, a_hi + 8u, bh, idesc, 1u);
                                 mma_ts_pair_elect(regD, a_hi, bl, idesc, 1u);
