@@ -391,6 +391,31 @@ def test_reverse_engine_range_scale_with_large_weights(golden, gain):
     assert err["tc_reverse"][1] <= max(TOL_ANGLE, 4 * err["simt"][1])
 
 
+@pytest.mark.parametrize("gain", [1.0, 3.0, 8.0])
+def test_forward_over_reverse_hessian_with_large_weights(golden, gain):
+    """The order-2 engine under the same stress: hidden weights scaled up (|H| reaches 1e6 at gain 8).  The tangent rows of the
+    backward sweep ride on the reverse engine's range scale: every output stays finite (the second-order forward jet overflows
+    FP16 at gain 8) and the Hessian error stays within 4x of the FP32 engine's own distance to fp64."""
+    import inf3dp
+    torch.manual_seed(5)
+    net = inf3dp.SingleBVPNet(type="sine", in_features=3)
+    with torch.no_grad():
+        for i in (1, 2, 3):
+            net.net.net[i][0].weight.mul_(gain)
+    net.cuda()
+    layers = so.params_from_state_dict({k: v.detach().cpu().numpy() for k, v in net.state_dict().items()})
+    g = torch.Generator().manual_seed(1)
+    x = (torch.rand(4096, 3, generator=g) * 2 - 1).cuda()
+    _, _, Ho = so.siren_jet(layers, x.cpu().numpy().astype(np.float64), order=2)
+    rel = {}
+    for eng in ("simt", "tc_reverse"):
+        y, J, H = net.query(x, order=2, mode=eng)
+        assert torch.isfinite(y).all() and torch.isfinite(J).all() and torch.isfinite(H).all()
+        Hn = H.cpu().numpy()[:, 0]
+        rel[eng] = (np.linalg.norm((Hn - Ho[:, 0]).reshape(len(Hn), -1), axis=1) / np.linalg.norm(Ho[:, 0].reshape(len(Hn), -1), axis=1)).max()
+    assert rel["tc_reverse"] <= max(1e-4, 4 * rel["simt"])
+
+
 @pytest.mark.gpu
 def test_packed_rows_equal_value_and_gradient(golden):
     """inf3dp_siren_value_grad_rows / inf3dp_unit_normals_rows: the packed (value, grad) rows are bit-identical to the
