@@ -342,9 +342,8 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
             if (lane == 0) { if (CTAS == 2) mbar_arrive_cluster(a_ready_base + 8u * (uint32_t)t); else mbar_arrive(a_ready_base + 8u * (uint32_t)t); }
         };
         auto publish = [&](int mi) {   // the slice just stored is visible to the MMA issuer
-            tc_wait_st();
+            tc_wait_st();          // .sync.aligned: the whole warp's stores have completed when any lane gets past it
             tc_fence_before();
-            __syncwarp();
             if (lane == 0) { if (CTAS == 2) mbar_arrive_cluster(a_ready_addr[mi]); else mbar_arrive(a_ready_addr[mi]); }
         };
 
@@ -405,7 +404,7 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
             for (int o = 0; o < kMlpMaxOut; ++o) acc[o] = 0.f;
             {
                 const float inv = s_misc[0];
-                mbar_wait_warp(bar(C::kBarDFull), dphase, lane, pd);
+                mbar_wait_timed(bar(C::kBarDFull), dphase, pd);   // every lane polls (one polling lane + __syncwarp wakes the warp later)
                 dphase ^= 1u;
                 tc_fence_after();
                 uint32_t v[16];
@@ -524,7 +523,7 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
                 const float inv = s_misc[g];
                 // out = [value] sin z  +  [first, second] cos z * (own / S)  -  [second] 2^-4 sin z (dz_i / S)(dz_j / S)
                 const float kb = (sel_1 + sel_2) * inv, kc = -(sel_2 * kR2) * inv * inv;
-                mbar_wait_warp(bar(C::kBarDFull), dphase, lane, pd);
+                mbar_wait_timed(bar(C::kBarDFull), dphase, pd);   // every lane polls (one polling lane + __syncwarp wakes the warp later)
                 dphase ^= 1u;
                 tc_fence_after();
                 uint32_t v[16];
@@ -642,7 +641,7 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
                     load_point(it + 1, npt, nvalid, nx, ny, nz);
                     s_next[0] = nx; s_next[1] = ny; s_next[2] = nz;
                 }
-                mbar_wait_warp(bar(C::kBarDFull), dphase, lane, pd);
+                mbar_wait_timed(bar(C::kBarDFull), dphase, pd);   // every lane polls (one polling lane + __syncwarp wakes the warp later)
                 dphase ^= 1u;
                 tc_fence_after();
                 uint32_t v[8];
@@ -776,7 +775,7 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
 #pragma unroll
                     for (int j = 0; j < 4; ++j) cs[j] = ld_keep4(sp + j * 128, stash_keep);
                 }
-                mbar_wait_warp(bar(C::kBarDFull), dphase, lane, pd);
+                mbar_wait_timed(bar(C::kBarDFull), dphase, pd);   // every lane polls (one polling lane + __syncwarp wakes the warp later)
                 dphase ^= 1u;
                 tc_fence_after();
                 uint32_t v[16];
@@ -1000,7 +999,7 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
                     const float4* sp = stash_at(4 - g, tp);
                     csa = ld_keep4(sp, stash_keep); csb = ld_keep4(sp + 128, stash_keep);
                 }
-                mbar_wait_warp(bar(C::kBarDFull), dphase, lane, pd);
+                mbar_wait_timed(bar(C::kBarDFull), dphase, pd);   // every lane polls (one polling lane + __syncwarp wakes the warp later)
                 dphase ^= 1u;
                 tc_fence_after();
                 const bool trace = dbg && blockIdx.x == 0 && it == 4 && warp == kFirstEpiWarp && lane == 0;

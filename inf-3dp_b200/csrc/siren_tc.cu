@@ -279,7 +279,7 @@ siren_tc_kernel(const char* __restrict__ packed, SirenHeader h, const float* __r
                 const float k1 = (ORDER == 1 && c != 0) ? inv_scale : 0.f;
                 const float k0 = (ORDER == 1 && c != 0) ? 0.f : 1.f;
                 const float* bl = s_bias + l * 512;
-                mbar_wait_warp(bar(kBarDFull), dphase, lane, pd);
+                mbar_wait_timed(bar(kBarDFull), dphase, pd);   // every lane polls (one polling lane + __syncwarp wakes the warp later)
                 dphase ^= 1u;
                 tc_fence_after();
                 uint32_t v[16];
