@@ -342,8 +342,9 @@ siren_rev_kernel(const char* __restrict__ packed, SirenHeader h, const float* __
             if (lane == 0) { if (CTAS == 2) mbar_arrive_cluster(a_ready_base + 8u * (uint32_t)t); else mbar_arrive(a_ready_base + 8u * (uint32_t)t); }
         };
         auto publish = [&](int mi) {   // the slice just stored is visible to the MMA issuer
-            tc_wait_st();          // .sync.aligned: the whole warp's stores have completed when any lane gets past it
+            tc_wait_st();
             tc_fence_before();
+            __syncwarp();
             if (lane == 0) { if (CTAS == 2) mbar_arrive_cluster(a_ready_addr[mi]); else mbar_arrive(a_ready_addr[mi]); }
         };
 
