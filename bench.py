@@ -407,7 +407,7 @@ def bench_intersection(dev, peaks, rank, world, extras):
     import numpy as np
     import torch
     import inf3dp
-    from inf3dp.dist import shard_range, all_gather_rows
+    from inf3dp.dist import sharded_fields_intersection
     from inf3dp.testing import CORNER_OFFSETS
     D, Ns, N1, N2 = 255, 500, 128, 128
     lin = torch.linspace(-1, 1, D + 1, device=dev)
@@ -426,15 +426,7 @@ def bench_intersection(dev, peaks, rank, world, extras):
                                                                 "(slice_toolpath.py:125)", "D": D, "isovalues": [Ns, N1, N2]},
            "cells_hit": int(m0.sum().item()), "launches_per_call": 4}
     if world > 1:
-        lo, hi, per = shard_range(Ns, rank, world)
-
-        def sharded():
-            m, i, p = inf3dp.get_fields_intersection_inter_slice(*fields, isos[0][lo:hi].contiguous(), isos[1], isos[2], centers, sync=False)
-            i = i.clone()
-            i[..., 0] += lo * (i[..., 0] >= 0).to(i.dtype)      # local slice index -> global slice index
-            return (all_gather_rows(m.view(hi - lo, -1).to(torch.uint8), Ns).view(Ns, N1, N2).bool(),
-                    all_gather_rows(i.view(hi - lo, -1), Ns).view(Ns, N1, N2, 3),
-                    all_gather_rows(p.view(hi - lo, -1), Ns).view(Ns, N1, N2, 3))
+        sharded = lambda: sharded_fields_intersection(*fields, *isos, centers)     # local slice index -> global, 3 all-gathers
         ms_sh, (gm, gi, gp) = _timeit(sharded, dev, 2, 5)
         ms_sh = _max_over_ranks(ms_sh, dev, world)
         if not (torch.equal(gm, m0) and torch.equal(gi, i0) and torch.equal(gp.nan_to_num(), p0.nan_to_num())):
@@ -472,7 +464,7 @@ def bench_hessian_sweep(net, dev, peaks, rank, world):
     N > 1: points sharded, principal curvatures and directions all-gathered (strong scaling)."""
     import torch
     import inf3dp
-    from inf3dp.dist import shard_range, all_gather_rows
+    from inf3dp.dist import shard_range, sharded_curvature_sweep
     n = 16_777_216
     g = torch.Generator(device="cpu").manual_seed(0)
     chunk = 1 << 22
@@ -484,12 +476,7 @@ def bench_hessian_sweep(net, dev, peaks, rank, world):
         if a < b:
             x[a - lo:b - lo] = piece[a - h:b - h].to(dev)
 
-    def sweep():
-        y, J, H = net.query(x, order=2)
-        kap, dirs = inf3dp.principal_curvatures(J[:, 0], H[:, 0])
-        if world > 1:
-            return all_gather_rows(kap, n), all_gather_rows(dirs.view(-1, 6), n)
-        return kap, dirs
+    sweep = lambda: sharded_curvature_sweep(net, x, presharded=True, n_total=n)   # order-2 query + curvature tail (+ all-gather)
     ms, (kap, dirs) = _timeit(sweep, dev, 2, 3)
     ms = _max_over_ranks(ms, dev, world)
     flop = 3_938_816        # Hessian mode as a forward jet of 1 + 3 + 6 columns (the figure the survey states)
@@ -521,7 +508,7 @@ def bench_collision(sdf_net, dev, rank, world, n_waypoints=4_194_304, m_nozzle=6
     import math
     import torch
     import inf3dp
-    from inf3dp.dist import shard_range, all_gather_rows
+    from inf3dp.dist import shard_range, sharded_quat_collision_sweep
     torch.manual_seed(2048)
     nets = [inf3dp.SingleBVPNet(type="sine", in_features=3, out_features=o) for o in (1, 1, 1, 1, 4)]
     slice_net, quat_net = nets[1].to(dev), nets[4].to(dev)
@@ -541,11 +528,8 @@ def bench_collision(sdf_net, dev, rank, world, n_waypoints=4_194_304, m_nozzle=6
     t = torch.linspace(0, 1, m_nozzle)
     nozzle = (torch.stack([0.5 * t * torch.cos(t * 40), 0.5 * t * torch.sin(t * 40), 0.2 + 4.0 * t], 1) / 150.0 * 20.0).to(dev)
 
-    def sweep():
-        d, h = inf3dp.quat_collision_sweep(way, levels, maxsl, nozzle, quat_net, sdf, slice_net, level, 8, -0.9)
-        if world > 1:
-            return all_gather_rows(d, n_waypoints), all_gather_rows(h.to(torch.uint8), n_waypoints).bool()
-        return d, h
+    sweep = lambda: sharded_quat_collision_sweep(way, levels, maxsl, nozzle, quat_net, sdf, slice_net, level, 8, -0.9,
+                                                 presharded=True, n_total=n_waypoints)
     ms, (depth, hit) = _timeit(sweep, dev, 1, 1)
     ms = _max_over_ranks(ms, dev, world)
     out = {"metric": "collision_waypoints_per_s", "value": n_waypoints / (ms / 1e3), "unit": "waypoints/s", "ms_per_sweep": ms,
@@ -564,12 +548,8 @@ def bench_collision(sdf_net, dev, rank, world, n_waypoints=4_194_304, m_nozzle=6
         nw = 65536
         a, b, _ = shard_range(nw, rank, world)
 
-        def sweep_shell():
-            d, h = inf3dp.quat_collision_sweep(way[a:b], levels[a:b], maxsl[a:b], shell, quat_net, sdf, slice_net, level, 8, -0.9,
-                                               waypoint_chunk=4096)
-            if world > 1:
-                return all_gather_rows(d, nw), all_gather_rows(h.to(torch.uint8), nw).bool()
-            return d, h
+        sweep_shell = lambda: sharded_quat_collision_sweep(way[a:b], levels[a:b], maxsl[a:b], shell, quat_net, sdf, slice_net, level,
+                                                           8, -0.9, presharded=True, n_total=nw, waypoint_chunk=4096)
         ms2, (d2, h2) = _timeit(sweep_shell, dev, 0, 1)
         ms2 = _max_over_ranks(ms2, dev, world)
         out["reference_nozzle"] = {"nozzle": "data/rect_nozzle_shell.xyz[::10] / 150 (6419 points, the reference's test nozzle)",

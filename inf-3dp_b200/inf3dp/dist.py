@@ -23,9 +23,14 @@ def all_gather_rows(local, n_total, group=None):
         return local
     rank = dist.get_rank(group)
     lo, hi, per = shard_range(n_total, rank, world)
+    if local.shape[0] != hi - lo:
+        raise RuntimeError(f"all_gather_rows: rank {rank} passed {local.shape[0]} rows, its shard of {n_total} is [{lo}, {hi})")
     if local.dtype in (torch.int16, torch.bool, torch.uint16):   # not NCCL dtypes: gather the rows as bytes
         tail = tuple(local.shape[1:])
-        raw = local.contiguous().view(hi - lo, -1).view(torch.uint8)
+        width = 1
+        for t in tail:
+            width *= int(t)
+        raw = local.contiguous().view(hi - lo, width).view(torch.uint8)      # explicit width: an empty shard has no -1
         return all_gather_rows(raw, n_total, group).view(local.dtype).view((n_total,) + tail)
     pad = torch.zeros((per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
     pad[:hi - lo] = local
@@ -94,6 +99,108 @@ def sharded_isocontours_compact(vertices, faces, fields, iso_values, group=None)
         a, b, _ = shard_range(K, r, world)
         shift[a:b] = base[r]
     return rows_all, offs_all + shift, counts_all, nums_all
+
+
+def _world_rank(group):
+    if not dist.is_initialized():
+        return 1, 0
+    return dist.get_world_size(group), dist.get_rank(group)
+
+
+def sharded_fields_intersection(slice_fields, lattice1_fields, lattice2_fields, slice_iso_values, lattice1_iso_values,
+                                lattice2_iso_values, voxel_centers, group=None, gather=True, sync=False):
+    """get_fields_intersection_inter_slice with the SLICE isovalues sharded (output dim 0; intersection.cu:227-287 treats
+    every (slice, lattice1, lattice2) cell independently).  The field grids are replicated, every rank intersects its
+    ceil(Ns / world) slice isovalues with all lattice isovalues, and the three outputs are all-gathered on dim 0.  The
+    slice component of `isovalue_indices` is local to the shard as the kernel writes it; it is shifted to the global
+    slice index where the cell holds an intersection (>= 0), the -1 of empty cells stays.
+    -> [inter_mask bool [Ns,N1,N2], isovalue_indices int16 [Ns,N1,N2,3], intersections f32 [Ns,N1,N2,3]], identical on
+    every rank and identical to the single-GPU call (gather=False: the local [hi-lo,N1,N2,...] slabs, indices global)."""
+    from . import contours
+    world, rank = _world_rank(group)
+    Ns, N1, N2 = slice_iso_values.numel(), lattice1_iso_values.numel(), lattice2_iso_values.numel()
+    lo, hi, _ = shard_range(Ns, rank, world)
+    if hi > lo:
+        m, i, p = contours.get_fields_intersection_inter_slice(slice_fields, lattice1_fields, lattice2_fields,
+                                                               slice_iso_values[lo:hi].contiguous(), lattice1_iso_values,
+                                                               lattice2_iso_values, voxel_centers, sync=sync)
+    else:   # more ranks than slice isovalues: this rank contributes no rows
+        dev = slice_fields.device
+        m = torch.zeros((0, N1, N2), dtype=torch.bool, device=dev)
+        i = torch.zeros((0, N1, N2, 3), dtype=torch.int16, device=dev)
+        p = torch.zeros((0, N1, N2, 3), dtype=torch.float32, device=dev)
+    if world == 1:
+        return [m, i, p]
+    i = i.clone()
+    i[..., 0] += lo * (i[..., 0] >= 0).to(i.dtype)
+    if not gather:
+        return [m, i, p]
+    return [all_gather_rows(m.view(hi - lo, N1 * N2), Ns, group).view(Ns, N1, N2),
+            all_gather_rows(i.view(hi - lo, N1 * N2 * 3), Ns, group).view(Ns, N1, N2, 3),
+            all_gather_rows(p.view(hi - lo, N1 * N2 * 3), Ns, group).view(Ns, N1, N2, 3)]
+
+
+def sharded_quat_collision_sweep(waypts, waypt_levels, current_level_maxslice, nozzle_pcd, quat_decoder, sdf_decoder,
+                                 slice_decoder, level_decoder, num_classes, base_th, group=None, gather=True, presharded=False,
+                                 n_total=None, **kw):
+    """inf3dp.quat_collision_sweep with the WAYPOINTS sharded (level_collision.py:259-281 evaluates every waypoint on its
+    own: quaternion field -> posed nozzle cloud -> TV-SDF predicates -> per-waypoint depth and mask).  The five networks
+    and the nozzle cloud are replicated; every rank sweeps waypoints shard_range(N, rank, world) and the per-waypoint
+    depth [N] and mask [N] are all-gathered.
+    presharded=False: `waypts`, `waypt_levels`, `current_level_maxslice` hold all N waypoints on every rank (this rank's
+    rows are sliced out here).  presharded=True: they hold this rank's shard only and `n_total` = N.
+    -> (depth f32 [N], hit bool [N]), identical on every rank (gather=False: the local shard's)."""
+    from . import collision
+    world, rank = _world_rank(group)
+    if presharded:
+        if n_total is None:
+            raise RuntimeError("sharded_quat_collision_sweep: presharded=True needs n_total")
+        n = int(n_total)
+        lo, hi, _ = shard_range(n, rank, world)
+        if waypts.shape[0] != hi - lo:
+            raise RuntimeError(f"sharded_quat_collision_sweep: rank {rank} holds {waypts.shape[0]} waypoints, its shard of "
+                               f"{n} is [{lo}, {hi})")
+        w, l, s = waypts, waypt_levels, current_level_maxslice
+    else:
+        n = waypts.shape[0]
+        lo, hi, _ = shard_range(n, rank, world)
+        w, l, s = waypts[lo:hi], waypt_levels[lo:hi], current_level_maxslice[lo:hi]
+    d, h = collision.quat_collision_sweep(w, l, s, nozzle_pcd, quat_decoder, sdf_decoder, slice_decoder, level_decoder,
+                                          num_classes, base_th, **kw)
+    if world == 1 or not gather:
+        return d, h
+    return all_gather_rows(d, n, group), all_gather_rows(h, n, group)
+
+
+def sharded_curvature_sweep(net, coords, group=None, gather=True, presharded=False, n_total=None, mode=None):
+    """The min / max-curvature field of a SIREN over N points with the POINTS sharded (SURVEY.md 8d cfg 5): value +
+    gradient + Hessian of this rank's points (order-2 query), the closed-form principal curvatures and directions
+    (diff_operators.py:27-44 + utils.py min_max_curvs_and_vectors), then one all-gather of [N,2] and [N,2,3].
+    presharded as in sharded_quat_collision_sweep.  -> (kappa [N,2], dirs [N,2,3])."""
+    from . import diffops
+    world, rank = _world_rank(group)
+    if presharded:
+        if n_total is None:
+            raise RuntimeError("sharded_curvature_sweep: presharded=True needs n_total")
+        n = int(n_total)
+        lo, hi, _ = shard_range(n, rank, world)
+        if coords.shape[0] != hi - lo:
+            raise RuntimeError(f"sharded_curvature_sweep: rank {rank} holds {coords.shape[0]} points, its shard of {n} is "
+                               f"[{lo}, {hi})")
+        x = coords
+    else:
+        n = coords.shape[0]
+        lo, hi, _ = shard_range(n, rank, world)
+        x = coords[lo:hi]
+    if hi > lo:
+        _, J, H = net.query(x, order=2, mode=mode)
+        kap, dirs = diffops.principal_curvatures(J[:, 0], H[:, 0])
+    else:   # more ranks than points
+        kap = torch.zeros((0, 2), dtype=torch.float32, device=coords.device)
+        dirs = torch.zeros((0, 2, 3), dtype=torch.float32, device=coords.device)
+    if world == 1 or not gather:
+        return kap, dirs
+    return all_gather_rows(kap, n, group), all_gather_rows(dirs.reshape(hi - lo, 6), n, group).view(n, 2, 3)
 
 
 class PipelinedAllGather:

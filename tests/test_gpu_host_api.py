@@ -125,3 +125,48 @@ def test_sharding_helpers_at_world_size_one(golden):
     m, k = idist.sharded_isocontours(*t)
     m0, k0 = inf3dp.extract_isocontours(*t)
     assert torch.equal(m, m0) and torch.equal(k, k0)
+
+
+def test_slice_waypoint_and_curvature_wrappers_at_world_size_one(golden):
+    """inf3dp.dist.sharded_fields_intersection / sharded_quat_collision_sweep / sharded_curvature_sweep on a single rank are
+    the plain device calls, bit for bit (their N > 1 exchange: tests/test_dist_gloo.py on gloo, bench.py --gpus N on NCCL)."""
+    import copy
+    import inf3dp
+    from inf3dp import dist as idist
+    from inf3dp.testing import corner_expanded_fields
+    dev = torch.device("cuda:0")
+    (sf, af, bf), centers = corner_expanded_fields(12)
+    isos = (np.linspace(-0.9, 0.9, 17).astype(np.float32), np.linspace(-0.8, 0.8, 7).astype(np.float32),
+            np.linspace(-0.8, 0.8, 5).astype(np.float32))
+    t = [torch.from_numpy(a).to(dev) for a in (sf, af, bf, *isos, centers)]
+    m0, i0, p0 = inf3dp.get_fields_intersection_inter_slice(*t)
+    m1, i1, p1 = idist.sharded_fields_intersection(*t, sync=True)
+    assert torch.equal(m0, m1) and torch.equal(i0, i1) and torch.equal(p0.nan_to_num(), p1.nan_to_num())
+    assert int(m0.sum()) > 0
+
+    net = _net(golden)
+    x = _points(5000, seed=5).cuda()
+    _, J, H = net.query(x, order=2)
+    k0, d0 = inf3dp.principal_curvatures(J[:, 0], H[:, 0])
+    k1, d1 = idist.sharded_curvature_sweep(net, x)
+    k2, d2 = idist.sharded_curvature_sweep(net, x, presharded=True, n_total=5000)
+    assert torch.equal(k0, k1) and torch.equal(d0, d1) and torch.equal(k0, k2) and torch.equal(d0, d2)
+    with pytest.raises(RuntimeError, match="its shard of"):
+        idist.sharded_curvature_sweep(net, x, presharded=True, n_total=4999)
+
+    torch.manual_seed(2048)
+    others = [inf3dp.SingleBVPNet(type="sine", in_features=3, out_features=o).to(dev) for o in (1, 1, 1, 1, 4)]
+    lvl = inf3dp.MLPClassifier(num_classes=8).to(dev)
+    sdf = copy.deepcopy(net)
+    with torch.no_grad():
+        sdf.net.net[4][0].bias -= 0.06
+    way = x[:300].clamp(-0.5, 0.5)
+    noz = (torch.rand((16, 3), generator=torch.Generator().manual_seed(1)) * 0.1).to(dev)
+    lev = torch.arange(300, device=dev) % 8
+    msl = torch.zeros((300, 8), device=dev)
+    a = inf3dp.quat_collision_sweep(way, lev, msl, noz, others[4], sdf, others[1], lvl, 8, -0.9)
+    b = idist.sharded_quat_collision_sweep(way, lev, msl, noz, others[4], sdf, others[1], lvl, 8, -0.9)
+    c = idist.sharded_quat_collision_sweep(way, lev, msl, noz, others[4], sdf, others[1], lvl, 8, -0.9, presharded=True,
+                                           n_total=300, waypoint_chunk=128)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[1], c[1])
+    assert float((a[0] - c[0]).abs().max()) <= 1e-6
