@@ -198,3 +198,63 @@ def test_sharded_wrappers_single_process_pass_through():
         assert k.shape == (6, 2) and dirs.shape == (6, 2, 3)
     finally:
         contours.get_fields_intersection_inter_slice, collision.quat_collision_sweep, diffops.principal_curvatures = saved
+
+
+# --- isovalue split (dense and compact exchange) and point split of the plain query, on gloo with CPU stand-ins
+
+def _fake_compact(vertices, faces, fields, iso_values):
+    """Row streams like extract_isocontours_compact: isovalue v owns n(v) rows filled with v, streams in isovalue order, the row
+    buffer larger than what is used (as the real one: capacity, not size)."""
+    K = iso_values.numel()
+    counts = ((iso_values * 10).round().long().abs() % 5 + 1).to(torch.int32) if K else torch.zeros(0, dtype=torch.int32)
+    offs = torch.cumsum(counts.long(), 0) - counts.long()
+    rows = torch.full((int(counts.sum()) + 7, 3), -7.0)
+    for k in range(K):
+        rows[offs[k]: offs[k] + counts[k]] = iso_values[k]
+    nums = (counts // 2).to(torch.int32)
+    return rows, offs, counts, nums
+
+
+def _fake_dense(vertices, faces, fields, iso_values, sync=True, want_seg_counts=False):
+    K, F = iso_values.numel(), faces.shape[0]
+    merged = iso_values.view(K, 1, 1).expand(K, F, 3).contiguous() if K else torch.zeros((0, F, 3))
+    return merged, (iso_values * 100).round().to(torch.int32)
+
+
+class _FakeFieldNet:
+    def query(self, x, order=1, mode=None):
+        return x.sum(1, keepdim=True), (2 * x).unsqueeze(1), None
+
+
+def _iso_worker(rank, world, port, K, n):
+    sys.path.insert(0, os.path.join(ROOT, "inf-3dp_b200"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from inf3dp import contours
+    from inf3dp import dist as idist
+    contours.extract_isocontours_compact = _fake_compact
+    contours.extract_isocontours_raw = _fake_dense
+    V, F = torch.zeros((4, 3)), torch.zeros((6, 3), dtype=torch.int32)
+    iso = torch.linspace(-0.83, 0.91, K)
+    rows, offs, counts, nums = idist.sharded_isocontours_compact(V, F, torch.zeros(4), iso)
+    w_rows, w_offs, w_counts, w_nums = _fake_compact(V, F, None, iso)
+    assert offs.dtype == torch.int64 and counts.dtype == torch.int32
+    assert torch.equal(counts, w_counts) and torch.equal(nums, w_nums), rank
+    assert rows.shape[0] == int(w_counts.sum())                      # only used rows travelled, no padding in between
+    for k in range(K):                                               # every stream sits where its global offset says
+        got = rows[offs[k]: offs[k] + counts[k]]
+        assert got.shape[0] == int(w_counts[k]) and bool((got == iso[k]).all()), (rank, k)
+    assert torch.equal(offs, w_offs)                                 # contiguous shards => the same packing as one rank's
+    merged, dn = idist.sharded_isocontours(V, F, torch.zeros(4), iso)
+    wm, wn = _fake_dense(V, F, None, iso)
+    assert torch.equal(merged, wm) and torch.equal(dn, wn), rank
+    x = torch.rand((n, 3), generator=torch.Generator().manual_seed(3))
+    got = idist.sharded_value_grad(_FakeFieldNet(), x)
+    assert torch.equal(got, torch.cat([x.sum(1, keepdim=True), 2 * x], 1)), rank
+    dist.destroy_process_group()
+
+
+def test_isovalue_split_dense_and_compact_and_point_split_world2():
+    for j, (K, n) in enumerate(((7, 13), (8, 16), (1, 1))):
+        mp.spawn(_iso_worker, args=(2, 29641 + j, K, n), nprocs=2, join=True)
